@@ -1,0 +1,304 @@
+// GEMM  C = beta*C + alpha * A * B^T  (NT: both operands K-contiguous) -- the BLAS-3 engine of the Cholesky
+// trailing update (SYRK, lower tiles only), the panel updates, the recursive TRSM and the posterior covariance.
+//
+// fp64: 128 x 128 x 16 CTA tile, 8 warps (2 x 4), each warp a 64 x 32 tile of DMMA.8x8x4 fragments (fp64 tensor
+//   cores; tcgen05 has no f64 kind).  Operands are staged by a 4-stage cp.async (LDGSTS) pipeline into a
+//   FRAGMENT-MAJOR shared-memory layout: the 16-byte granule holding (row, k = 2j, 2j+1) is stored where lane
+//   (row % 8) * 4 + j of the owning 8-row block reads it, so every fragment load is one conflict-free,
+//   warp-contiguous LDS.128 that feeds TWO DMMAs (the even-k one and the odd-k one -- the k order inside a
+//   k-group of 8 is permuted identically for A and B, which leaves the product unchanged).
+//   Roofline: fp64 tensor pipe (measured 37.1 TFLOP/s DMMA peak); algorithmic flops 2 M N K (M N K for lower).
+// fp32: classic register-tiled FFMA kernel (8 x 8 micro-tiles), double-buffered.
+#include "common.cuh"
+
+namespace gpk {
+
+constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 16, GM_STAGES = 4, GM_THREADS = 256;
+constexpr int GM_STAGE_ELEMS = GM_BM * GM_BK;  // per operand per stage
+
+template <typename T>
+struct GemmParams {
+  int64_t M, N, K;
+  T alpha, beta;
+  const T* A;
+  int64_t lda, a_bs;
+  const T* B;
+  int64_t ldb, b_bs;
+  T* C;
+  int64_t ldc, c_bs;
+  int32_t lower;
+  int32_t tiles_m, tiles_n;
+};
+
+// CTA -> tile mapping: groups of 8 tile-rows are walked column-by-column so that concurrently resident CTAs
+// share A and B panels in L2.
+__device__ __forceinline__ void tile_coords(int id, int tiles_m, int tiles_n, int& tm, int& tn) {
+  const int GROUP = 8;
+  const int per_group = GROUP * tiles_n;
+  const int group = id / per_group;
+  const int first_m = group * GROUP;
+  const int gsize = min(tiles_m - first_m, GROUP);
+  const int r = id - group * per_group;
+  tm = first_m + r % gsize;
+  tn = r / gsize;
+}
+
+__global__ void __launch_bounds__(GM_THREADS, 1) gemm_nt_f64_kernel(const GemmParams<double> p) {
+  int tm, tn;
+  tile_coords(blockIdx.x, p.tiles_m, p.tiles_n, tm, tn);
+  if (p.lower && tn > tm) return;
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps; warp tile 64 x 32
+
+  extern __shared__ __align__(16) double gm_smem[];
+  double* As = gm_smem;
+  double* Bs = gm_smem + GM_STAGES * GM_STAGE_ELEMS;
+
+  const double* Ag = p.A + (int64_t)b * p.a_bs + (int64_t)tm * GM_BM * p.lda;
+  const double* Bg = p.B + (int64_t)b * p.b_bs + (int64_t)tn * GM_BN * p.ldb;
+
+  // each thread copies 4 granules of A and 4 of B per stage: rows (tid / 8) + 32 i, granule g = tid % 8
+  const int ld_row = tid >> 3, ld_g = tid & 7;
+  const int ld_slot = ((ld_g >> 2) * 32 + (ld_row & 7) * 4 + (ld_g & 3)) * 2;  // + (row / 8) * 128 per row block
+  auto load_stage = [&](int slot, int kt) {
+    const int64_t koff = (int64_t)kt * GM_BK + ld_g * 2;
+    double* as = As + slot * GM_STAGE_ELEMS;
+    double* bs = Bs + slot * GM_STAGE_ELEMS;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = ld_row + 32 * i;
+      const int dst = (row >> 3) * 128 + ld_slot;
+      cp_async16(as + dst, Ag + (int64_t)row * p.lda + koff);
+      cp_async16(bs + dst, Bg + (int64_t)row * p.ldb + koff);
+    }
+  };
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int KT = (int)(p.K / GM_BK);
+#pragma unroll
+  for (int s = 0; s < GM_STAGES - 1; ++s) {
+    if (s < KT) load_stage(s, s);
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<GM_STAGES - 2>();
+    __syncthreads();
+    {
+      const int nk = kt + GM_STAGES - 1;
+      if (nk < KT) load_stage(nk % GM_STAGES, nk);
+      cp_async_commit();
+    }
+    const double* as = As + (kt % GM_STAGES) * GM_STAGE_ELEMS + (wm * 8) * 128 + lane * 2;
+    const double* bs = Bs + (kt % GM_STAGES) * GM_STAGE_ELEMS + (wn * 4) * 128 + lane * 2;
+#pragma unroll
+    for (int k8 = 0; k8 < 2; ++k8) {
+      double2 a[8], bb[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const double2*>(as + i * 128 + k8 * 64);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = *reinterpret_cast<const double2*>(bs + j * 128 + k8 * 64);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dmma884(acc[i][j][0], acc[i][j][1], a[i].x, bb[j].x);
+          dmma884(acc[i][j][0], acc[i][j][1], a[i].y, bb[j].y);
+        }
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: lane holds C[row = lane / 4][col = 2 (lane % 4) + {0, 1}] of every 8 x 8 fragment
+  double* Cg = p.C + (int64_t)b * p.c_bs + ((int64_t)tm * GM_BM + wm * 64 + (lane >> 2)) * p.ldc +
+               (int64_t)tn * GM_BN + wn * 32 + 2 * (lane & 3);
+  const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double2* cp = reinterpret_cast<double2*>(Cg + (int64_t)i * 8 * p.ldc + j * 8);
+      double2 v;
+      if (beta != 0.0) {
+        const double2 old = *cp;
+        v.x = fma(alpha, acc[i][j][0], beta * old.x);
+        v.y = fma(alpha, acc[i][j][1], beta * old.y);
+      } else {
+        v.x = alpha * acc[i][j][0];
+        v.y = alpha * acc[i][j][1];
+      }
+      *cp = v;
+    }
+}
+
+// ---- fp32: register-tiled FFMA ------------------------------------------------------------------------
+constexpr int SG_BK = 16;
+
+__global__ void __launch_bounds__(GM_THREADS, 2) gemm_nt_f32_kernel(const GemmParams<float> p) {
+  int tm, tn;
+  tile_coords(blockIdx.x, p.tiles_m, p.tiles_n, tm, tn);
+  if (p.lower && tn > tm) return;
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  __shared__ __align__(16) float As[2][SG_BK][GM_BM + 4];
+  __shared__ __align__(16) float Bs[2][SG_BK][GM_BN + 4];
+
+  const float* Ag = p.A + (int64_t)b * p.a_bs + (int64_t)tm * GM_BM * p.lda;
+  const float* Bg = p.B + (int64_t)b * p.b_bs + (int64_t)tn * GM_BN * p.ldb;
+
+  // global -> registers: each thread fetches 2 float4 of A and 2 of B per k-tile (128 rows x 16 k = 512 float4)
+  const int lr = tid >> 2, lk = (tid & 3) * 4;  // rows lr, lr + 64; k offset lk
+  float4 ra[2], rb[2];
+  auto gload = [&](int kt) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      ra[i] = *reinterpret_cast<const float4*>(Ag + (int64_t)(lr + 64 * i) * p.lda + (int64_t)kt * SG_BK + lk);
+      rb[i] = *reinterpret_cast<const float4*>(Bg + (int64_t)(lr + 64 * i) * p.ldb + (int64_t)kt * SG_BK + lk);
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = lr + 64 * i;
+      As[buf][lk + 0][r] = ra[i].x;
+      As[buf][lk + 1][r] = ra[i].y;
+      As[buf][lk + 2][r] = ra[i].z;
+      As[buf][lk + 3][r] = ra[i].w;
+      Bs[buf][lk + 0][r] = rb[i].x;
+      Bs[buf][lk + 1][r] = rb[i].y;
+      Bs[buf][lk + 2][r] = rb[i].z;
+      Bs[buf][lk + 3][r] = rb[i].w;
+    }
+  };
+
+  const int tx = tid & 15, ty = tid >> 4;  // thread tile: rows ty*4 + {0..3} and 64 + ty*4 + {0..3}; cols likewise with tx
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int KT = (int)(p.K / SG_BK);
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < KT; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < KT) gload(kt + 1);
+#pragma unroll
+    for (int k = 0; k < SG_BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < KT) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  float* Cg = p.C + (int64_t)b * p.c_bs + (int64_t)tm * GM_BM * p.ldc + (int64_t)tn * GM_BN;
+  const float alpha = p.alpha, beta = p.beta;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      float4* cp = reinterpret_cast<float4*>(Cg + (int64_t)r * p.ldc + jh * 64 + tx * 4);
+      float4 v;
+      if (beta != 0.f) {
+        const float4 o = *cp;
+        v.x = fmaf(alpha, acc[i][jh * 4 + 0], beta * o.x);
+        v.y = fmaf(alpha, acc[i][jh * 4 + 1], beta * o.y);
+        v.z = fmaf(alpha, acc[i][jh * 4 + 2], beta * o.z);
+        v.w = fmaf(alpha, acc[i][jh * 4 + 3], beta * o.w);
+      } else {
+        v.x = alpha * acc[i][jh * 4 + 0];
+        v.y = alpha * acc[i][jh * 4 + 1];
+        v.z = alpha * acc[i][jh * 4 + 2];
+        v.w = alpha * acc[i][jh * 4 + 3];
+      }
+      *cp = v;
+    }
+  }
+}
+
+template <typename T>
+static int check_gemm_args(int64_t M, int64_t N, int64_t K, const T* A, int64_t lda, const T* B, int64_t ldb, T* C,
+                           int64_t ldc, int32_t batch) {
+  if (M < 0 || N < 0 || K < 0 || batch < 1 || !A || !B || !C) return GPK_ERR_ARG;
+  if (M % GM_BM || N % GM_BN || K % GM_BK) return GPK_ERR_ARG;
+  if (lda < K || ldb < K || ldc < N) return GPK_ERR_ARG;
+  const int64_t al = 16 / sizeof(T);
+  if (lda % al || ldb % al || ldc % al) return GPK_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) % 16)
+    return GPK_ERR_ALIGN;
+  return 0;
+}
+
+int gemm_nt_f64(int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, int64_t a_bs,
+                const double* B, int64_t ldb, int64_t b_bs, double beta, double* C, int64_t ldc, int64_t c_bs,
+                int32_t lower, int32_t batch, cudaStream_t stream) {
+  int rc = check_gemm_args<double>(M, N, K, A, lda, B, ldb, C, ldc, batch);
+  if (rc) return rc;
+  if (M == 0 || N == 0) return 0;
+  GemmParams<double> p{M, N, K, alpha, beta, A, lda, a_bs, B, ldb, b_bs, C, ldc, c_bs, lower,
+                       (int32_t)(M / GM_BM), (int32_t)(N / GM_BN)};
+  static bool attr_set = false;
+  const int smem = 2 * GM_STAGES * GM_STAGE_ELEMS * (int)sizeof(double);
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_nt_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return -1000 - (int)e;
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch);
+  gemm_nt_f64_kernel<<<grid, GM_THREADS, smem, stream>>>(p);
+  GPK_COUNT_LAUNCH();
+  GPK_CHECK_LAUNCH();
+  return 0;
+}
+
+int gemm_nt_f32(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, int64_t a_bs,
+                const float* B, int64_t ldb, int64_t b_bs, float beta, float* C, int64_t ldc, int64_t c_bs,
+                int32_t lower, int32_t batch, cudaStream_t stream) {
+  int rc = check_gemm_args<float>(M, N, K, A, lda, B, ldb, C, ldc, batch);
+  if (rc) return rc;
+  if (M == 0 || N == 0) return 0;
+  GemmParams<float> p{M, N, K, alpha, beta, A, lda, a_bs, B, ldb, b_bs, C, ldc, c_bs, lower,
+                      (int32_t)(M / GM_BM), (int32_t)(N / GM_BN)};
+  dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch);
+  gemm_nt_f32_kernel<<<grid, GM_THREADS, 0, stream>>>(p);
+  GPK_COUNT_LAUNCH();
+  GPK_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace gpk
+
+extern "C" {
+int gpk_gemm_nt_f64(int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, int64_t a_bstride,
+                    const double* B, int64_t ldb, int64_t b_bstride, double beta, double* C, int64_t ldc,
+                    int64_t c_bstride, int32_t lower, int32_t batch, void* stream) {
+  return gpk::gemm_nt_f64(M, N, K, alpha, A, lda, a_bstride, B, ldb, b_bstride, beta, C, ldc, c_bstride, lower, batch,
+                          (cudaStream_t)stream);
+}
+int gpk_gemm_nt_f32(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, int64_t a_bstride,
+                    const float* B, int64_t ldb, int64_t b_bstride, float beta, float* C, int64_t ldc,
+                    int64_t c_bstride, int32_t lower, int32_t batch, void* stream) {
+  return gpk::gemm_nt_f32(M, N, K, alpha, A, lda, a_bstride, B, ldb, b_bstride, beta, C, ldc, c_bstride, lower, batch,
+                          (cudaStream_t)stream);
+}
+}

@@ -1,0 +1,390 @@
+// K1: fused pairwise-distance + kernel-evaluation kernel (sm_100a).
+//
+// One CTA produces a 64 x 64 tile of K.  The pre-stretched input rows of the tile (x^(g) and y^(g) for every
+// lengthscale group g) are staged into shared memory by the TMA engine with 1-D bulk async copies
+// (cp.async.bulk + mbarrier; SASS UBLKCP), falling back to plain loads for unaligned / ragged tiles.  Every
+// thread owns a 4 x 4 micro-tile (columns strided by 16 so that a half-warp reads conflict-free shared memory
+// and writes one contiguous 128-byte (fp64) row segment per store), evaluates the flattened sum-of-products kernel
+// expression in registers and writes K exactly once, with the observation noise, the Cholesky jitter and the
+// identity padding fused in.  In LOWER mode tiles above the diagonal are skipped (halves the exp work and the
+// HBM writes).  Roofline: HBM-write bound (8 n^2 bytes, 4 n^2 in LOWER mode), close to the fp64-ALU ridge.
+//
+// Reference arithmetic replaced: mlkernels.pairwise for EQ/Matern/Linear/Delta and Scaled/Sum/Product/Stretched
+// (call sites stheno/model/fdd.py:79, stheno/model/observations.py:139,285,286), Dense + Diagonal (fdd.py:79)
+// and B.reg's "+ epsilon I" (README.md:820-830).
+#include "common.cuh"
+
+namespace gpk {
+
+constexpr int KM_TILE = 64;
+constexpr int KM_THREADS = 256;
+
+struct KmParams {
+  gpk_kernel_desc desc;
+  const void* xg;
+  const void* yg;
+  int64_t xg_gstride, x_bstride, yg_gstride, y_bstride;
+  int64_t n, n2;
+  int32_t d;
+  double noise_scalar;
+  const void* noise_vec;
+  int64_t nv_bstride;
+  double jitter;
+  int32_t flags;
+  void* out;
+  int64_t ldo, o_bstride;
+  int64_t rows_out, cols_out;
+};
+
+template <typename T>
+__device__ __forceinline__ T t_exp(T v);
+template <>
+__device__ __forceinline__ double t_exp<double>(double v) {
+  return exp(v);
+}
+template <>
+__device__ __forceinline__ float t_exp<float>(float v) {
+  return expf(v);
+}
+template <typename T>
+__device__ __forceinline__ T t_sqrt(T v);
+template <>
+__device__ __forceinline__ double t_sqrt<double>(double v) {
+  return sqrt(v);
+}
+template <>
+__device__ __forceinline__ float t_sqrt<float>(float v) {
+  return sqrtf(v);
+}
+
+// phi(kind) from squared distance d2 / dot product.  d == 1 mirrors lab's |x - y| special case (no 1e-30 clamp).
+template <typename T>
+__device__ __forceinline__ T eval_factor(int kind, T d2, T dot, bool same_point, bool same_obj, int d) {
+  switch (kind) {
+    case GPK_EQ:
+      return t_exp<T>(T(-0.5) * d2);
+    case GPK_MATERN12: {
+      T r = (d == 1) ? t_sqrt<T>(d2) : t_sqrt<T>(d2 > T(1e-30) ? d2 : T(1e-30));
+      return t_exp<T>(-r);
+    }
+    case GPK_MATERN32: {
+      T r = (d == 1) ? t_sqrt<T>(d2) : t_sqrt<T>(d2 > T(1e-30) ? d2 : T(1e-30));
+      T s = T(1.7320508075688772) * r;
+      return (T(1) + s) * t_exp<T>(-s);
+    }
+    case GPK_MATERN52: {
+      T r = (d == 1) ? t_sqrt<T>(d2) : t_sqrt<T>(d2 > T(1e-30) ? d2 : T(1e-30));
+      T s = T(2.23606797749979) * r;
+      return (T(1) + s + T(1.6666666666666667) * d2) * t_exp<T>(-s);
+    }
+    case GPK_LINEAR:
+      return dot;
+    case GPK_DELTA:
+      return same_obj ? (same_point ? T(1) : T(0)) : (d2 < T(1e-10) ? T(1) : T(0));
+    default:
+      return T(1);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(KM_THREADS) kernel_matrix_kernel(const KmParams p) {
+  const int tile_c = blockIdx.x, tile_r = blockIdx.y, b = blockIdx.z;
+  const bool lower = p.flags & GPK_KM_LOWER;
+  // LOWER: skip tiles strictly above the diagonal at 128-granularity (the Cholesky's tile size), so that every
+  // 128 x 128 diagonal tile is fully initialised.
+  if (lower && (tile_c >> 1) > (tile_r >> 1)) return;
+  const bool same_obj = p.flags & GPK_KM_SAME;
+  const int d = p.d;
+  const int G = p.desc.n_groups;
+  const int64_t r0 = (int64_t)tile_r * KM_TILE, c0 = (int64_t)tile_c * KM_TILE;
+
+  extern __shared__ __align__(16) unsigned char km_smem[];
+  __shared__ __align__(8) uint64_t bar;
+  T* xs = reinterpret_cast<T*>(km_smem);            // [G][64][d]
+  T* ys = xs + (size_t)G * KM_TILE * d;               // [G][64][d]
+  const T* xg = static_cast<const T*>(p.xg) + (int64_t)b * p.x_bstride;
+  const T* yg = static_cast<const T*>(p.yg) + (int64_t)b * p.y_bstride;
+
+  // rows of the tile that exist in the inputs (the rest is padding)
+  const int xr = (int)max((int64_t)0, min((int64_t)KM_TILE, p.n - r0));
+  const int yr = (int)max((int64_t)0, min((int64_t)KM_TILE, p.n2 - c0));
+  const uint32_t xbytes = (uint32_t)xr * d * sizeof(T), ybytes = (uint32_t)yr * d * sizeof(T);
+  // The bulk-copy engine needs 16-byte aligned addresses and sizes.
+  bool bulk = (xbytes % 16 == 0) && (ybytes % 16 == 0) && ((KM_TILE * d * sizeof(T)) % 16 == 0);
+  for (int g = 0; g < G && bulk; ++g) {
+    bulk = bulk && (reinterpret_cast<uintptr_t>(xg + g * p.xg_gstride + r0 * d) % 16 == 0) &&
+           (reinterpret_cast<uintptr_t>(yg + g * p.yg_gstride + c0 * d) % 16 == 0);
+  }
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_arrive_expect_tx(&bar, (uint32_t)G * (xbytes + ybytes));
+      for (int g = 0; g < G; ++g) {
+        if (xbytes) bulk_copy_g2s(xs + (size_t)g * KM_TILE * d, xg + g * p.xg_gstride + r0 * d, xbytes, &bar);
+        if (ybytes) bulk_copy_g2s(ys + (size_t)g * KM_TILE * d, yg + g * p.yg_gstride + c0 * d, ybytes, &bar);
+      }
+    }
+    mbar_wait(&bar, 0);
+  } else {
+    for (int g = 0; g < G; ++g) {
+      for (int i = threadIdx.x; i < xr * d; i += KM_THREADS)
+        xs[(size_t)g * KM_TILE * d + i] = xg[g * p.xg_gstride + r0 * d + i];
+      for (int i = threadIdx.x; i < yr * d; i += KM_THREADS)
+        ys[(size_t)g * KM_TILE * d + i] = yg[g * p.yg_gstride + c0 * d + i];
+    }
+    __syncthreads();
+  }
+
+  // Transpose the y rows to [g][k][64 (+1 pad)] so that the 16 column-threads of a half-warp read consecutive
+  // shared-memory words (the [row][d] image the bulk copy produces would be a d-word stride: bank conflicts).
+  T* yt = ys + (size_t)G * KM_TILE * d;  // [G][d][65]
+  for (int idx = threadIdx.x; idx < G * KM_TILE * d; idx += KM_THREADS) {
+    const int g = idx / (KM_TILE * d), rem = idx - g * KM_TILE * d;
+    const int c = rem / d, k = rem - c * d;
+    yt[((size_t)g * d + k) * (KM_TILE + 1) + c] = ys[idx];
+  }
+  __syncthreads();
+
+  // thread (tx, ty): rows r0 + 4*ty + i, columns c0 + tx + 16*j  (i, j < 4)
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+
+  T d2[4][4], dt[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      d2[i][j] = T(0);
+      dt[i][j] = T(0);
+    }
+  int last_g = -1;
+  for (int t = 0; t < p.desc.n_terms; ++t) {
+    T prod[4][4];
+    const T coef = (T)p.desc.coef[t];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) prod[i][j] = coef;
+    for (int f = p.desc.term_begin[t]; f < p.desc.term_begin[t + 1]; ++f) {
+      const int kind = p.desc.fac_kind[f];
+      const int g = p.desc.fac_group[f];
+      if (g != last_g && kind != GPK_ONE && !(kind == GPK_DELTA && same_obj)) {
+        last_g = g;
+        const T* xr_ = xs + ((size_t)g * KM_TILE + ty * 4) * d;
+        const T* yc_ = yt + (size_t)g * d * (KM_TILE + 1) + tx;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            d2[i][j] = T(0);
+            dt[i][j] = T(0);
+          }
+        for (int k = 0; k < d; ++k) {
+          T xv[4], yv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xv[i] = xr_[i * d + k];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) yv[j] = yc_[(size_t)k * (KM_TILE + 1) + 16 * j];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              T df = xv[i] - yv[j];
+              d2[i][j] = fma(df, df, d2[i][j]);
+              dt[i][j] = fma(xv[i], yv[j], dt[i][j]);
+            }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool same_pt = (r0 + ty * 4 + i) == (c0 + tx + 16 * j);
+          prod[i][j] *= eval_factor<T>(kind, d2[i][j], dt[i][j], same_pt, same_obj, d);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += prod[i][j];
+  }
+
+  // epilogue: diagonal terms, identity / zero padding; a half-warp writes 128 (fp64) / 64 (fp32) contiguous bytes
+  T* out = static_cast<T*>(p.out) + (int64_t)b * p.o_bstride;
+  const T* nv = p.noise_vec ? static_cast<const T*>(p.noise_vec) + (int64_t)b * p.nv_bstride : nullptr;
+  const bool pad_id = p.flags & GPK_KM_PAD_IDENTITY;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + ty * 4 + i;
+    if (r >= p.rows_out) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t c = c0 + tx + 16 * j;
+      if (c >= p.cols_out) continue;
+      T val = acc[i][j];
+      if (r >= p.n || c >= p.n2) {
+        val = (pad_id && r == c) ? T(1) : T(0);
+      } else if (same_obj && r == c) {
+        val += (T)p.noise_scalar;
+        if (nv) val += nv[r];
+        val += (T)p.jitter;
+      }
+      out[r * p.ldo + c] = val;
+    }
+  }
+}
+
+template <typename T>
+static int launch_kernel_matrix(const gpk_kernel_desc* desc, const T* xg, int64_t xg_gstride, int64_t x_bstride,
+                                int64_t n, const T* yg, int64_t yg_gstride, int64_t y_bstride, int64_t n2, int32_t d,
+                                double noise_scalar, const T* noise_vec, int64_t nv_bstride, double jitter,
+                                int32_t flags, T* out, int64_t ldo, int64_t o_bstride, int32_t batch, void* stream) {
+  if (!desc || !xg || !yg || !out || n < 0 || n2 < 0 || d < 1 || batch < 1) return GPK_ERR_ARG;
+  if (desc->n_terms < 0 || desc->n_terms > GPK_MAX_TERMS || desc->n_groups < 1 || desc->n_groups > GPK_MAX_GROUPS)
+    return GPK_ERR_ARG;
+  if (desc->term_begin[desc->n_terms] > GPK_MAX_FACTORS) return GPK_ERR_ARG;
+  const bool pad = flags & (GPK_KM_PAD_IDENTITY | GPK_KM_PAD_ZERO);
+  KmParams p;
+  p.desc = *desc;
+  p.xg = xg;
+  p.yg = yg;
+  p.xg_gstride = xg_gstride;
+  p.x_bstride = x_bstride;
+  p.yg_gstride = yg_gstride;
+  p.y_bstride = y_bstride;
+  p.n = n;
+  p.n2 = n2;
+  p.d = d;
+  p.noise_scalar = noise_scalar;
+  p.noise_vec = noise_vec;
+  p.nv_bstride = nv_bstride;
+  p.jitter = jitter;
+  p.flags = flags;
+  p.out = out;
+  p.ldo = ldo;
+  p.o_bstride = o_bstride;
+  p.rows_out = pad ? gpk_round_up(n) : n;
+  p.cols_out = pad ? gpk_round_up(n2) : n2;
+  if (p.rows_out == 0 || p.cols_out == 0) return 0;
+  if (ldo < p.cols_out) return GPK_ERR_ARG;
+  const size_t smem = ((size_t)2 * desc->n_groups * KM_TILE * d + (size_t)desc->n_groups * d * (KM_TILE + 1)) * sizeof(T);
+  if (smem > 200 * 1024) return GPK_ERR_UNSUPPORTED;
+  auto kern = kernel_matrix_kernel<T>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -1000 - (int)e;
+  }
+  dim3 grid((unsigned)((p.cols_out + KM_TILE - 1) / KM_TILE), (unsigned)((p.rows_out + KM_TILE - 1) / KM_TILE),
+            (unsigned)batch);
+  if (grid.y > 65535 || grid.z > 65535) return GPK_ERR_UNSUPPORTED;
+  kern<<<grid, KM_THREADS, smem, (cudaStream_t)stream>>>(p);
+  GPK_COUNT_LAUNCH();
+  GPK_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---- elwise ------------------------------------------------------------------------------------------
+struct KdParams {
+  gpk_kernel_desc desc;
+  const void* xg;
+  const void* yg;
+  int64_t xg_gstride, x_bstride, yg_gstride, y_bstride, n;
+  int32_t d, same;
+  void* out;
+  int64_t o_bstride;
+};
+
+template <typename T>
+__global__ void kernel_diag_kernel(const KdParams p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (i >= p.n) return;
+  const T* xg = static_cast<const T*>(p.xg) + (int64_t)b * p.x_bstride;
+  const T* yg = static_cast<const T*>(p.yg) + (int64_t)b * p.y_bstride;
+  T acc = T(0);
+  for (int t = 0; t < p.desc.n_terms; ++t) {
+    T prod = (T)p.desc.coef[t];
+    for (int f = p.desc.term_begin[t]; f < p.desc.term_begin[t + 1]; ++f) {
+      const int g = p.desc.fac_group[f];
+      const T* xr = xg + g * p.xg_gstride + i * p.d;
+      const T* yr = yg + g * p.yg_gstride + i * p.d;
+      T d2 = T(0), dt = T(0);
+      for (int k = 0; k < p.d; ++k) {
+        T df = xr[k] - yr[k];
+        d2 = fma(df, df, d2);
+        dt = fma(xr[k], yr[k], dt);
+      }
+      prod *= eval_factor<T>(p.desc.fac_kind[f], d2, dt, true, p.same != 0, p.d);
+    }
+    acc += prod;
+  }
+  static_cast<T*>(p.out)[(int64_t)b * p.o_bstride + i] = acc;
+}
+
+template <typename T>
+static int launch_kernel_diag(const gpk_kernel_desc* desc, const T* xg, int64_t xg_gstride, int64_t x_bstride,
+                              const T* yg, int64_t yg_gstride, int64_t y_bstride, int64_t n, int32_t d, int32_t same,
+                              T* out, int64_t o_bstride, int32_t batch, void* stream) {
+  if (!desc || !xg || !yg || !out || n < 0 || d < 1 || batch < 1) return GPK_ERR_ARG;
+  if (n == 0) return 0;
+  KdParams p;
+  p.desc = *desc;
+  p.xg = xg;
+  p.yg = yg;
+  p.xg_gstride = xg_gstride;
+  p.x_bstride = x_bstride;
+  p.yg_gstride = yg_gstride;
+  p.y_bstride = y_bstride;
+  p.n = n;
+  p.d = d;
+  p.same = same;
+  p.out = out;
+  p.o_bstride = o_bstride;
+  dim3 grid((unsigned)((n + 255) / 256), (unsigned)batch);
+  kernel_diag_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  GPK_COUNT_LAUNCH();
+  GPK_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace gpk
+
+extern "C" {
+
+int gpk_kernel_matrix_f64(const gpk_kernel_desc* desc_host, const double* xg, int64_t xg_gstride, int64_t x_bstride,
+                          int64_t n, const double* yg, int64_t yg_gstride, int64_t y_bstride, int64_t n2, int32_t d,
+                          double noise_scalar, const double* noise_vec, int64_t nv_bstride, double jitter,
+                          int32_t flags, double* out, int64_t ldo, int64_t o_bstride, int32_t batch, void* stream) {
+  return gpk::launch_kernel_matrix<double>(desc_host, xg, xg_gstride, x_bstride, n, yg, yg_gstride, y_bstride, n2, d,
+                                           noise_scalar, noise_vec, nv_bstride, jitter, flags, out, ldo, o_bstride,
+                                           batch, stream);
+}
+int gpk_kernel_matrix_f32(const gpk_kernel_desc* desc_host, const float* xg, int64_t xg_gstride, int64_t x_bstride,
+                          int64_t n, const float* yg, int64_t yg_gstride, int64_t y_bstride, int64_t n2, int32_t d,
+                          double noise_scalar, const float* noise_vec, int64_t nv_bstride, double jitter,
+                          int32_t flags, float* out, int64_t ldo, int64_t o_bstride, int32_t batch, void* stream) {
+  return gpk::launch_kernel_matrix<float>(desc_host, xg, xg_gstride, x_bstride, n, yg, yg_gstride, y_bstride, n2, d,
+                                          noise_scalar, noise_vec, nv_bstride, jitter, flags, out, ldo, o_bstride,
+                                          batch, stream);
+}
+int gpk_kernel_diag_f64(const gpk_kernel_desc* desc_host, const double* xg, int64_t xg_gstride, int64_t x_bstride,
+                        const double* yg, int64_t yg_gstride, int64_t y_bstride, int64_t n, int32_t d, int32_t same,
+                        double* out, int64_t o_bstride, int32_t batch, void* stream) {
+  return gpk::launch_kernel_diag<double>(desc_host, xg, xg_gstride, x_bstride, yg, yg_gstride, y_bstride, n, d, same,
+                                         out, o_bstride, batch, stream);
+}
+int gpk_kernel_diag_f32(const gpk_kernel_desc* desc_host, const float* xg, int64_t xg_gstride, int64_t x_bstride,
+                        const float* yg, int64_t yg_gstride, int64_t y_bstride, int64_t n, int32_t d, int32_t same,
+                        float* out, int64_t o_bstride, int32_t batch, void* stream) {
+  return gpk::launch_kernel_diag<float>(desc_host, xg, xg_gstride, x_bstride, yg, yg_gstride, y_bstride, n, d, same,
+                                        out, o_bstride, batch, stream);
+}
+}

@@ -1,0 +1,363 @@
+// K2 / K3: blocked right-looking Cholesky (lower, row-major, in place) and the recursive triangular solve.
+//
+//   potrf      two-level blocking: 128-wide leaf steps inside 1024-wide outer panels.  Per leaf step
+//                (1) potrf_leaf  : one CTA factorises the 128 x 128 diagonal block entirely in registers
+//                                  (cyclic 8 x 8 micro-tiles, one __syncthreads per column, log-det and info folded in)
+//                (2) trsm_leaf   : all rows below (incl. the fused right-hand-side rows)  X L11^T = A21
+//                (3) gemm (K=128): update of the rest of the outer panel
+//              and per outer panel one big SYRK-style trailing update (K = 1024) on the fp64 tensor cores, which
+//              carries > 90 % of the n^3/3 flops at n = 16384 with C read/written once per 1024 columns.
+//   trsm_right recursive halving down to the 128-wide leaf; all off-diagonal work is gemm_nt with K >= 128.
+//
+// Right-hand sides ride along as extra ROWS below the matrix (b^T), so L^-1 b falls out of the factorisation
+// itself (B.iqf_diag's triangular solve, stheno/random.py:276) -- no separate TRSV launch chain.
+//
+// Reference arithmetic replaced: B.cholesky / B.logdet / B.solve (stheno/random.py:274-276,
+// stheno/model/observations.py:300-301,334).
+#include "common.cuh"
+
+namespace gpk {
+
+int gemm_nt_f64(int64_t, int64_t, int64_t, double, const double*, int64_t, int64_t, const double*, int64_t, int64_t,
+                double, double*, int64_t, int64_t, int32_t, int32_t, cudaStream_t);
+int gemm_nt_f32(int64_t, int64_t, int64_t, float, const float*, int64_t, int64_t, const float*, int64_t, int64_t,
+                float, float*, int64_t, int64_t, int32_t, int32_t, cudaStream_t);
+
+static inline int gemm_nt(int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, int64_t a_bs,
+                          const double* B, int64_t ldb, int64_t b_bs, double beta, double* C, int64_t ldc, int64_t c_bs,
+                          int32_t lower, int32_t batch, cudaStream_t s) {
+  return gemm_nt_f64(M, N, K, alpha, A, lda, a_bs, B, ldb, b_bs, beta, C, ldc, c_bs, lower, batch, s);
+}
+static inline int gemm_nt(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, int64_t a_bs,
+                          const float* B, int64_t ldb, int64_t b_bs, float beta, float* C, int64_t ldc, int64_t c_bs,
+                          int32_t lower, int32_t batch, cudaStream_t s) {
+  return gemm_nt_f32(M, N, K, alpha, A, lda, a_bs, B, ldb, b_bs, beta, C, ldc, c_bs, lower, batch, s);
+}
+
+constexpr int NB = 128;
+
+template <typename T>
+__device__ __forceinline__ T t_sqrt_(T v) {
+  return sizeof(T) == 8 ? (T)sqrt((double)v) : (T)sqrtf((float)v);
+}
+template <typename T>
+__device__ __forceinline__ T t_log_(T v) {
+  return sizeof(T) == 8 ? (T)log((double)v) : (T)logf((float)v);
+}
+
+// ---- leaf Cholesky: 128 x 128 block in registers ----------------------------------------------------------
+// thread (ti, tk) = (tid / 16, tid % 16) owns elements (i, k) = (ti + 16 a, tk + 16 b), a, b < 8.
+template <typename T>
+__global__ void __launch_bounds__(256, 1)
+potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int64_t a_bs, T* __restrict__ logdet, int32_t* __restrict__ info,
+                  int32_t pivot_base) {
+  const int bidx = blockIdx.x;
+  A += (int64_t)bidx * a_bs;
+  const int tid = threadIdx.x, ti = tid >> 4, tk = tid & 15;
+  __shared__ T colbuf[2][NB];
+  __shared__ T diag[NB];
+  __shared__ T red[8];
+
+  T acc[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b] = A[(int64_t)(ti + 16 * a) * lda + tk + 16 * b];
+
+  int buf = 0;
+#pragma unroll
+  for (int jb = 0; jb < 8; ++jb) {
+    for (int jj = 0; jj < 16; ++jj) {
+      const int j = jj + 16 * jb;
+      if (tk == jj) {
+#pragma unroll
+        for (int a = 0; a < 8; ++a) colbuf[buf][ti + 16 * a] = acc[a][jb];
+      }
+      __syncthreads();
+      const T djj = colbuf[buf][j];
+      if (tid == 0 && !(djj > T(0))) atomicCAS(info + bidx, 0, pivot_base + j + 1);
+      const T dsq = t_sqrt_<T>(djj);
+      const T inv = T(1) / dsq;
+      T li[8], lk[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) li[a] = colbuf[buf][ti + 16 * a] * inv;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) lk[b] = colbuf[buf][tk + 16 * b] * inv;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        if (b < jb) continue;
+        const bool col_ok = (b > jb) || (tk > jj);
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          if (a < b) continue;
+          const bool ok = col_ok && ((a > b) || (ti >= tk));
+          if (ok) acc[a][b] -= li[a] * lk[b];
+        }
+      }
+      if (tk == jj) {  // finalise column j of L
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          const int i = ti + 16 * a;
+          if (i > j) acc[a][jb] = li[a];
+          else if (i == j) acc[a][jb] = dsq;
+        }
+      }
+      if (tid == 0) diag[j] = dsq;
+      buf ^= 1;
+    }
+  }
+
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int i = ti + 16 * a, k = tk + 16 * b;
+      if (i >= k) A[(int64_t)i * lda + k] = acc[a][b];
+    }
+
+  __syncthreads();
+  if (logdet != nullptr) {
+    T v = (tid < NB) ? t_log_<T>(diag[tid]) : T(0);
+    v = warp_sum(v);
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+      T s = T(0);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w];
+      atomicAdd(logdet + bidx, T(2) * s);
+    }
+  }
+}
+
+// ---- leaf TRSM:  X L^T = B  (B: rows x 128, 64 rows per CTA), in place ----------------------------------------
+// thread (r, cg) = (tid % 64, tid / 64) owns row r, columns 32 cg .. 32 cg + 31 in registers.
+// UPPER == true solves X L = B instead (backward substitution; L still lower-triangular).
+constexpr int TL_LD = NB + 2;
+
+template <typename T, bool TRANS>
+__global__ void __launch_bounds__(256, 1)
+trsm_leaf_kernel(const T* __restrict__ L, int64_t ldl, int64_t l_bs, T* __restrict__ B, int64_t ldb, int64_t b_bs) {
+  extern __shared__ __align__(16) unsigned char tl_smem[];
+  T* Lt = reinterpret_cast<T*>(tl_smem);  // !TRANS: Lt[j][k] = L[k][j];  TRANS: Lt[j][k] = L[j][k]   (ld = TL_LD)
+  T* invd = Lt + NB * TL_LD;              // 1 / L[j][j]
+  T* xbuf = invd + NB;                    // [2][64]
+  const int tid = threadIdx.x;
+  const int bidx = blockIdx.y;
+  L += (int64_t)bidx * l_bs;
+  B += (int64_t)bidx * b_bs + (int64_t)blockIdx.x * 64 * ldb;
+
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int k = idx >> 7, j = idx & 127;  // read L[k][j] coalesced in j
+    const T v = (j <= k) ? L[(int64_t)k * ldl + j] : T(0);
+    if (!TRANS) Lt[j * TL_LD + k] = v;
+    else Lt[k * TL_LD + j] = v;
+    if (j == k) invd[j] = T(1) / v;
+  }
+  const int r = tid & 63, cg = tid >> 6;
+  T a[32];
+  {
+    const T* src = B + (int64_t)r * ldb + 32 * cg;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) a[q] = src[q];
+  }
+  __syncthreads();
+
+  int buf = 0;
+  for (int step = 0; step < NB; ++step) {
+    // forward: j = 0..127 ; backward (TRANS): j = 127..0
+    const int j = TRANS ? (NB - 1 - step) : step;
+    const int cgj = j >> 5, jj = j & 31;
+    if (cg == cgj) {
+      T x = T(0);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) x = (q == jj) ? a[q] : x;
+      x *= invd[j];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) a[q] = (q == jj) ? x : a[q];
+      xbuf[buf * 64 + r] = x;
+    }
+    __syncthreads();
+    const bool active = TRANS ? (cg <= cgj) : (cg >= cgj);
+    if (active) {
+      const T x = xbuf[buf * 64 + r];
+      // !TRANS: a[k] -= x * L[k][j] (k > j) = Lt[j][k];  TRANS: a[k] -= x * L[j][k] (k < j) = Lt[j][k]
+      const T* lrow = Lt + j * TL_LD + 32 * cg;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const bool ok = (cg != cgj) || (TRANS ? (q < jj) : (q > jj));
+        if (ok) a[q] -= x * lrow[q];
+      }
+    }
+    buf ^= 1;
+  }
+  {
+    T* dst = B + (int64_t)r * ldb + 32 * cg;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) dst[q] = a[q];
+  }
+}
+
+template <typename T>
+static int launch_potrf_leaf(T* A, int64_t lda, int64_t a_bs, T* logdet, int32_t* info, int32_t pivot_base,
+                             int32_t batch, cudaStream_t stream) {
+  potrf_leaf_kernel<T><<<batch, 256, 0, stream>>>(A, lda, a_bs, logdet, info, pivot_base);
+  GPK_COUNT_LAUNCH();
+  GPK_CHECK_LAUNCH();
+  return 0;
+}
+
+template <typename T, bool TRANS>
+static int launch_trsm_leaf(const T* L, int64_t ldl, int64_t l_bs, T* B, int64_t ldb, int64_t b_bs, int64_t rows,
+                            int32_t batch, cudaStream_t stream) {
+  if (rows == 0) return 0;
+  const int smem = (NB * TL_LD + NB + 2 * 64) * (int)sizeof(T);
+  auto kern = trsm_leaf_kernel<T, TRANS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return -1000 - (int)e;
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(rows / 64), (unsigned)batch);
+  kern<<<grid, 256, smem, stream>>>(L, ldl, l_bs, B, ldb, b_bs);
+  GPK_COUNT_LAUNCH();
+  GPK_CHECK_LAUNCH();
+  return 0;
+}
+
+constexpr int64_t NB_OUTER = 1024;
+
+template <typename T>
+static int potrf_driver(T* A, int64_t lda, int64_t a_bs, int64_t n_pad, int64_t extra_rows, T* logdet, int32_t* info,
+                        int32_t batch, cudaStream_t stream) {
+  if (!A || n_pad < 0 || extra_rows < 0 || batch < 1 || !info) return GPK_ERR_ARG;
+  if (n_pad % NB || extra_rows % NB || lda < n_pad) return GPK_ERR_ARG;
+  if (lda % (16 / sizeof(T)) || reinterpret_cast<uintptr_t>(A) % 16) return GPK_ERR_ALIGN;
+  const int64_t R = n_pad + extra_rows;
+  int rc;
+  for (int64_t kb = 0; kb < n_pad; kb += NB_OUTER) {
+    const int64_t ke = (kb + NB_OUTER < n_pad) ? kb + NB_OUTER : n_pad;
+    for (int64_t j = kb; j < ke; j += NB) {
+      T* Ajj = A + j * lda + j;
+      if ((rc = launch_potrf_leaf<T>(Ajj, lda, a_bs, logdet, info, (int32_t)j, batch, stream))) return rc;
+      const int64_t below = R - (j + NB);
+      if (below > 0) {
+        T* A21 = A + (j + NB) * lda + j;
+        if ((rc = launch_trsm_leaf<T, false>(Ajj, lda, a_bs, A21, lda, a_bs, below, batch, stream))) return rc;
+        const int64_t ncols = ke - (j + NB);
+        if (ncols > 0) {
+          if ((rc = gemm_nt(below, ncols, (int64_t)NB, T(-1), A21, lda, a_bs, A21, lda, a_bs, T(1),
+                            A + (j + NB) * lda + (j + NB), lda, a_bs, 1, batch, stream)))
+            return rc;
+        }
+      }
+    }
+    if (ke < n_pad) {
+      const T* P = A + ke * lda + kb;
+      if ((rc = gemm_nt(R - ke, n_pad - ke, ke - kb, T(-1), P, lda, a_bs, P, lda, a_bs, T(1), A + ke * lda + ke, lda,
+                        a_bs, 1, batch, stream)))
+        return rc;
+    }
+  }
+  return 0;
+}
+
+// X L^T = B, recursive halving (all sizes multiples of 128).
+template <typename T>
+static int trsm_right_rec(const T* L, int64_t ldl, int64_t l_bs, int64_t n, T* B, int64_t ldb, int64_t b_bs,
+                          int64_t rows, int32_t batch, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (n == NB) return launch_trsm_leaf<T, false>(L, ldl, l_bs, B, ldb, b_bs, rows, batch, stream);
+  const int64_t h = ((n / NB) / 2) * NB;
+  int rc;
+  if ((rc = trsm_right_rec<T>(L, ldl, l_bs, h, B, ldb, b_bs, rows, batch, stream))) return rc;
+  if ((rc = gemm_nt(rows, n - h, h, T(-1), B, ldb, b_bs, L + h * ldl, ldl, l_bs, T(1), B + h, ldb, b_bs, 0, batch,
+                    stream)))
+    return rc;
+  return trsm_right_rec<T>(L + h * ldl + h, ldl, l_bs, n - h, B + h, ldb, b_bs, rows, batch, stream);
+}
+
+template <typename T>
+static int trsm_right_driver(const T* L, int64_t ldl, int64_t l_bs, int64_t n_pad, T* B, int64_t ldb, int64_t b_bs,
+                             int64_t rows, int32_t batch, cudaStream_t stream) {
+  if (!L || !B || n_pad < 0 || rows < 0 || batch < 1) return GPK_ERR_ARG;
+  if (n_pad % NB || rows % NB || ldl < n_pad || ldb < n_pad) return GPK_ERR_ARG;
+  if (ldl % (16 / sizeof(T)) || ldb % (16 / sizeof(T))) return GPK_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(L) | reinterpret_cast<uintptr_t>(B)) % 16) return GPK_ERR_ALIGN;
+  if (rows == 0) return 0;
+  return trsm_right_rec<T>(L, ldl, l_bs, n_pad, B, ldb, b_bs, rows, batch, stream);
+}
+
+// X L = B (backward substitution), right-looking over 128-blocks from the last to the first.  The off-diagonal
+// update  B[:, 0:j] -= X_j L[j, 0:j]  is a rank-128 "NN" product; it is expressed with gemm_nt through an explicit
+// transposed copy of the L row-panel made by the caller-provided scratch -- used only for few right-hand sides
+// (autograd, sparse mu), so the simple blocked form is enough.
+template <typename T>
+__global__ void trsm_t_update_kernel(const T* __restrict__ L, int64_t ldl, int64_t l_bs, T* __restrict__ B,
+                                     int64_t ldb, int64_t b_bs, int64_t j0, int64_t rows) {
+  // B[r][c] -= sum_{q < 128} B[r][j0 + q] * L[j0 + q][c]   for c < j0 ; one thread per (r, c)
+  const int bidx = blockIdx.z;
+  L += (int64_t)bidx * l_bs;
+  B += (int64_t)bidx * b_bs;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = blockIdx.y;
+  __shared__ T xs[NB];
+  if (threadIdx.x < NB) xs[threadIdx.x] = B[r * ldb + j0 + threadIdx.x];
+  __syncthreads();
+  if (c >= j0 || r >= rows) return;
+  T s = T(0);
+#pragma unroll 8
+  for (int q = 0; q < NB; ++q) s = fma(xs[q], L[(j0 + q) * ldl + c], s);
+  B[r * ldb + c] -= s;
+}
+
+template <typename T>
+static int trsm_right_t_driver(const T* L, int64_t ldl, int64_t l_bs, int64_t n_pad, T* B, int64_t ldb, int64_t b_bs,
+                               int64_t rows, int32_t batch, cudaStream_t stream) {
+  if (!L || !B || n_pad < 0 || rows < 0 || batch < 1) return GPK_ERR_ARG;
+  if (n_pad % NB || rows % 64 || ldl < n_pad || ldb < n_pad) return GPK_ERR_ARG;
+  if (rows == 0) return 0;
+  int rc;
+  for (int64_t j = n_pad - NB; j >= 0; j -= NB) {
+    if ((rc = launch_trsm_leaf<T, true>(L + j * ldl + j, ldl, l_bs, B + j, ldb, b_bs, rows, batch, stream))) return rc;
+    if (j > 0) {
+      dim3 grid((unsigned)((j + 127) / 128), (unsigned)rows, (unsigned)batch);
+      trsm_t_update_kernel<T><<<grid, 128, 0, stream>>>(L, ldl, l_bs, B, ldb, b_bs, j, rows);
+      GPK_COUNT_LAUNCH();
+      GPK_CHECK_LAUNCH();
+    }
+  }
+  return 0;
+}
+
+}  // namespace gpk
+
+extern "C" {
+int gpk_potrf_f64(double* A, int64_t lda, int64_t a_bstride, int64_t n_pad, int64_t extra_rows, double* logdet,
+                  int32_t* info, int32_t batch, void* stream) {
+  return gpk::potrf_driver<double>(A, lda, a_bstride, n_pad, extra_rows, logdet, info, batch, (cudaStream_t)stream);
+}
+int gpk_potrf_f32(float* A, int64_t lda, int64_t a_bstride, int64_t n_pad, int64_t extra_rows, float* logdet,
+                  int32_t* info, int32_t batch, void* stream) {
+  return gpk::potrf_driver<float>(A, lda, a_bstride, n_pad, extra_rows, logdet, info, batch, (cudaStream_t)stream);
+}
+int gpk_trsm_right_f64(const double* L, int64_t ldl, int64_t l_bstride, int64_t n_pad, double* B, int64_t ldb,
+                       int64_t b_bstride, int64_t rows, int32_t batch, void* stream) {
+  return gpk::trsm_right_driver<double>(L, ldl, l_bstride, n_pad, B, ldb, b_bstride, rows, batch, (cudaStream_t)stream);
+}
+int gpk_trsm_right_f32(const float* L, int64_t ldl, int64_t l_bstride, int64_t n_pad, float* B, int64_t ldb,
+                       int64_t b_bstride, int64_t rows, int32_t batch, void* stream) {
+  return gpk::trsm_right_driver<float>(L, ldl, l_bstride, n_pad, B, ldb, b_bstride, rows, batch, (cudaStream_t)stream);
+}
+int gpk_trsm_right_t_f64(const double* L, int64_t ldl, int64_t l_bstride, int64_t n_pad, double* B, int64_t ldb,
+                         int64_t b_bstride, int64_t rows, int32_t batch, void* stream) {
+  return gpk::trsm_right_t_driver<double>(L, ldl, l_bstride, n_pad, B, ldb, b_bstride, rows, batch,
+                                          (cudaStream_t)stream);
+}
+int gpk_trsm_right_t_f32(const float* L, int64_t ldl, int64_t l_bstride, int64_t n_pad, float* B, int64_t ldb,
+                         int64_t b_bstride, int64_t rows, int32_t batch, void* stream) {
+  return gpk::trsm_right_t_driver<float>(L, ldl, l_bstride, n_pad, B, ldb, b_bstride, rows, batch,
+                                         (cudaStream_t)stream);
+}
+}

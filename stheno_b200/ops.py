@@ -1,0 +1,390 @@
+"""Tensor-level operations of the GP hot path, executed by the hand-written sm_100a kernels of ``libgpk``.
+
+Everything here takes and returns CUDA ``torch`` tensors (PyTorch = device memory + streams; the arithmetic is
+in ``csrc/*.cu``).  There is no CPU implementation: calling an op with a CPU tensor raises.
+
+Storage conventions (see ``include/gpk.h``): row-major, batch-major ``[B, rows, cols]``; matrices that get
+factorised live in a workspace ``W[B, n_pad + extra, n_pad]`` padded to multiples of 128 with the identity, the
+``extra`` rows below the matrix carrying right-hand sides ``b^T`` that leave the factorisation as ``(L^-1 b)^T``.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import KIND, KM_LOWER, KM_PAD_IDENTITY, KM_PAD_ZERO, KM_SAME, GpkError, KernelDesc, check
+
+__all__ = [
+    "FlatKernel",
+    "Chol",
+    "round_up",
+    "kernel_matrix",
+    "kernel_diag",
+    "chol_from_kernel",
+    "chol_from_dense",
+    "gemm_nt",
+    "launch_count",
+]
+
+TILE = 128
+
+
+def round_up(n, m=TILE):
+    return (int(n) + m - 1) // m * m
+
+
+def _suffix(dtype):
+    if dtype == torch.float64:
+        return "f64"
+    if dtype == torch.float32:
+        return "f32"
+    raise TypeError(f"stheno_b200 computes in float64 or float32, got {dtype}")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "stheno_b200.ops: CUDA tensor required -- the hot path runs only on the sm_100a kernels "
+                "(there is no CPU fallback)"
+            )
+
+
+def _fn(name, dtype):
+    return getattr(_lib.load(), f"{name}_{_suffix(dtype)}")
+
+
+def launch_count(reset=False):
+    lib = _lib.load()
+    c = int(lib.gpk_launch_count())
+    if reset:
+        lib.gpk_launch_count_reset()
+    return c
+
+
+class FlatKernel:
+    """A kernel flattened to a sum of products of elementary kernels on pre-stretched inputs:
+    ``sum_t coef_t * prod_f kind_f(x / scale[group_f], y / scale[group_f])``.
+
+    ``terms`` is a list of ``(coef: float, [(kind: str, group: int), ...])``."""
+
+    def __init__(self, terms, n_groups):
+        self.terms = [(float(c), [(str(k), int(g)) for k, g in fs]) for c, fs in terms]
+        self.n_groups = max(int(n_groups), 1)
+        if len(self.terms) > _lib.GPK_MAX_TERMS:
+            raise GpkError(f"kernel expands to {len(self.terms)} product terms (limit {_lib.GPK_MAX_TERMS})")
+        if sum(len(fs) for _, fs in self.terms) > _lib.GPK_MAX_FACTORS:
+            raise GpkError(f"kernel has more than {_lib.GPK_MAX_FACTORS} elementary factors")
+        if self.n_groups > _lib.GPK_MAX_GROUPS:
+            raise GpkError(f"kernel uses more than {_lib.GPK_MAX_GROUPS} distinct length scales")
+
+    def desc(self):
+        d = KernelDesc()
+        d.n_terms = len(self.terms)
+        d.n_groups = self.n_groups
+        f = 0
+        for t, (coef, fs) in enumerate(self.terms):
+            d.term_begin[t] = f
+            d.coef[t] = coef
+            for kind, group in fs:
+                d.fac_kind[f] = KIND[kind]
+                d.fac_group[f] = group
+                f += 1
+        d.term_begin[len(self.terms)] = f
+        return d
+
+
+def _check_groups(xg, flat):
+    if xg.dim() != 4:
+        raise ValueError("scaled inputs must have shape [groups, batch, n, d]")
+    if xg.shape[0] < flat.n_groups:
+        raise ValueError("not enough input groups for the kernel")
+
+
+def _km_launch(flat, xg, yg, n, n2, d, flags, noise_scalar, noise_vec, jitter, out, ldo, o_bstride, batch):
+    _require_cuda(xg, yg, out, noise_vec)
+    xg = xg.contiguous()
+    yg = xg if yg is xg else yg.contiguous()
+    if noise_vec is not None:
+        noise_vec = noise_vec.contiguous()
+    desc = flat.desc()
+    rc = _fn("gpk_kernel_matrix", out.dtype)(
+        ctypes.byref(desc), _ptr(xg), xg.stride(0), xg.stride(1), n, _ptr(yg), yg.stride(0), yg.stride(1), n2, d,
+        float(noise_scalar), _ptr(noise_vec), (noise_vec.stride(0) if noise_vec is not None else 0), float(jitter),
+        flags, _ptr(out), ldo, o_bstride, batch, _stream(),
+    )
+    check(rc, "gpk_kernel_matrix")
+
+
+def kernel_matrix(flat, xg, yg=None, *, same=None, noise_scalar=0.0, noise_vec=None, jitter=0.0):
+    """Full ``[B, n, n2]`` kernel matrix ``k(x, y)`` (+ noise on the diagonal when ``same``).
+
+    ``xg``/``yg``: ``[G, B, n, d]`` pre-stretched inputs; ``yg=None`` means the same object as ``xg``."""
+    _check_groups(xg, flat)
+    if yg is None:
+        yg = xg
+        same = True if same is None else same
+    same = bool(same)
+    B, n, d = xg.shape[1], xg.shape[2], xg.shape[3]
+    n2 = yg.shape[2]
+    out = torch.empty(B, n, n2, device=xg.device, dtype=xg.dtype)
+    if n == 0 or n2 == 0:
+        return out
+    _km_launch(flat, xg, yg, n, n2, d, KM_SAME if same else 0, noise_scalar, noise_vec, jitter, out, n2, n * n2, B)
+    return out
+
+
+def kernel_diag(flat, xg, yg=None, *, same=None):
+    """``k.elwise(x, y)`` -> ``[B, n]``."""
+    _check_groups(xg, flat)
+    if yg is None:
+        yg, same = xg, (True if same is None else same)
+    _require_cuda(xg, yg)
+    xg = xg.contiguous()
+    yg = xg if yg is xg else yg.contiguous()
+    B, n, d = xg.shape[1], xg.shape[2], xg.shape[3]
+    out = torch.empty(B, n, device=xg.device, dtype=xg.dtype)
+    if n == 0:
+        return out
+    desc = flat.desc()
+    rc = _fn("gpk_kernel_diag", xg.dtype)(
+        ctypes.byref(desc), _ptr(xg), xg.stride(0), xg.stride(1), _ptr(yg), yg.stride(0), yg.stride(1), n, d,
+        1 if same else 0, _ptr(out), n, B, _stream(),
+    )
+    check(rc, "gpk_kernel_diag")
+    return out
+
+
+def gemm_nt(A, Bm, C=None, *, alpha=1.0, beta=0.0, lower=False):
+    """``C = beta * C + alpha * A @ Bm^T`` on padded ``[B, M, K]`` / ``[B, N, K]`` tensors (views with a unit inner
+    stride are fine).  Returns ``C``."""
+    _require_cuda(A, Bm, C)
+    Bn, M, K = A.shape
+    N = Bm.shape[1]
+    if C is None:
+        C = torch.empty(Bn, M, N, device=A.device, dtype=A.dtype)
+        beta = 0.0
+    for t in (A, Bm, C):
+        if t.stride(2) != 1:
+            raise ValueError("gemm_nt needs a unit inner stride")
+    rc = _fn("gpk_gemm_nt", A.dtype)(
+        M, N, K, alpha, _ptr(A), A.stride(1), A.stride(0), _ptr(Bm), Bm.stride(1), Bm.stride(0), beta, _ptr(C),
+        C.stride(1), C.stride(0), 1 if lower else 0, Bn, _stream(),
+    )
+    check(rc, "gpk_gemm_nt")
+    return C
+
+
+def _pad_copy(src, dst, rows, cols, rows_pad, cols_pad, diag_add, pad_identity):
+    rc = _fn("gpk_pad_copy", dst.dtype)(
+        _ptr(src), src.stride(1), src.stride(0), rows, cols, _ptr(dst), dst.stride(1), dst.stride(0), rows_pad,
+        cols_pad, float(diag_add), 1 if pad_identity else 0, dst.shape[0], _stream(),
+    )
+    check(rc, "gpk_pad_copy")
+
+
+def symmetrize_(A, n):
+    """Mirror the lower triangle of the leading ``n x n`` block into the upper one, in place."""
+    rc = _fn("gpk_symmetrize", A.dtype)(_ptr(A), A.stride(1), A.stride(0), n, A.shape[0], _stream())
+    check(rc, "gpk_symmetrize")
+    return A
+
+
+def transpose(src, rows, cols, out=None):
+    """``out[B, cols, rows] = src[B, rows, cols]^T`` (leading block of possibly padded tensors)."""
+    if out is None:
+        out = torch.empty(src.shape[0], cols, rows, device=src.device, dtype=src.dtype)
+    rc = _fn("gpk_transpose", src.dtype)(
+        _ptr(src), src.stride(1), src.stride(0), rows, cols, _ptr(out), out.stride(1), out.stride(0), src.shape[0],
+        _stream(),
+    )
+    check(rc, "gpk_transpose")
+    return out
+
+
+def row_dot_sq(V, rows, n_cols, b=None, want_dot=True, want_sq=True):
+    """Per-row ``<V[r, :n_cols], b>`` and ``|V[r, :n_cols]|^2`` of ``V[B, *, *]`` -> two ``[B, rows]`` tensors."""
+    Bn = V.shape[0]
+    dot = torch.empty(Bn, rows, device=V.device, dtype=V.dtype) if (want_dot and b is not None) else None
+    sq = torch.empty(Bn, rows, device=V.device, dtype=V.dtype) if want_sq else None
+    if rows == 0:
+        return dot, sq
+    if b is not None:
+        b = b.contiguous()
+    rc = _fn("gpk_row_dot_sq", V.dtype)(
+        _ptr(V), V.stride(1), V.stride(0), rows, n_cols, _ptr(b), (b.stride(0) if b is not None else 0), _ptr(dot),
+        _ptr(sq), rows, Bn, _stream(),
+    )
+    check(rc, "gpk_row_dot_sq")
+    return dot, sq
+
+
+class Chol:
+    """Lower Cholesky factor ``L`` of ``K + jitter I`` in padded workspace storage, with fused right-hand sides.
+
+    Attributes: ``W [B, n_pad + extra, n_pad]``, ``n``, ``n_pad``, ``k`` (number of fused right-hand sides),
+    ``logdet [B]`` (= ``2 sum log diag L``), ``info [B]`` (int32; first non-positive pivot, 0 = ok)."""
+
+    def __init__(self, W, n, k, logdet, info):
+        self.W, self.n, self.k, self.logdet, self.info = W, int(n), int(k), logdet, info
+        self.n_pad = W.shape[2]
+        self.batch = W.shape[0]
+
+    @property
+    def dtype(self):
+        return self.W.dtype
+
+    @property
+    def device(self):
+        return self.W.device
+
+    def check(self):
+        """Raise ``torch.linalg.LinAlgError`` if a pivot was non-positive (forces a host sync)."""
+        bad = self.info.nonzero()
+        if bad.numel():
+            b = int(bad[0, 0])
+            raise torch.linalg.LinAlgError(
+                f"Cholesky: leading minor of order {int(self.info[b])} is not positive definite (batch {b})"
+            )
+        return self
+
+    def L_padded(self):
+        return self.W[:, : self.n_pad, :]
+
+    def L(self):
+        """Dense ``[B, n, n]`` lower-triangular factor (copy; strict upper triangle zeroed)."""
+        return torch.tril(self.W[:, : self.n, : self.n])
+
+    def rhs_half(self):
+        """``(L^-1 rhs)^T`` for the fused right-hand sides: ``[B, k, n]`` (a view)."""
+        return self.W[:, self.n_pad : self.n_pad + self.k, : self.n]
+
+    def logpdf(self):
+        """``-0.5 (logdet + n log 2 pi + |L^-1 rhs_c|^2)`` for every fused right-hand side -> ``[B, k]``."""
+        if self.k == 0:
+            raise ValueError("no right-hand side was fused into this factorisation")
+        out = torch.empty(self.batch, self.k, device=self.device, dtype=self.dtype)
+        rows = self.W[:, self.n_pad :, :]
+        rc = _fn("gpk_logpdf_finish", self.dtype)(
+            _ptr(rows), rows.stride(1), rows.stride(0), self.n, self.n_pad, self.k, _ptr(self.logdet), _ptr(out),
+            self.batch, _stream(),
+        )
+        check(rc, "gpk_logpdf_finish")
+        return out
+
+    def new_rows(self, rows, zero=True):
+        """A padded ``[B, round_up(rows), n_pad]`` buffer for :meth:`solve_rows_`."""
+        f = torch.zeros if zero else torch.empty
+        return f(self.batch, round_up(rows), self.n_pad, device=self.device, dtype=self.dtype)
+
+    def solve_rows_(self, Bt):
+        """In place ``Bt <- Bt L^-T`` on a padded ``[B, rows_pad, n_pad]`` buffer: row r becomes ``(L^-1 b_r)^T``."""
+        _require_cuda(Bt)
+        if Bt.shape[2] != self.n_pad or Bt.shape[1] % TILE or Bt.stride(2) != 1:
+            raise ValueError("solve_rows_ needs a padded [B, rows_pad, n_pad] buffer")
+        Lp = self.L_padded()
+        rc = _fn("gpk_trsm_right", self.dtype)(
+            _ptr(Lp), Lp.stride(1), Lp.stride(0), self.n_pad, _ptr(Bt), Bt.stride(1), Bt.stride(0), Bt.shape[1],
+            self.batch, _stream(),
+        )
+        check(rc, "gpk_trsm_right")
+        return Bt
+
+    def solve_rows_t_(self, Bt):
+        """In place ``Bt <- Bt L^-1``: row r becomes ``(L^-T b_r)^T`` (backward substitution)."""
+        _require_cuda(Bt)
+        Lp = self.L_padded()
+        rc = _fn("gpk_trsm_right_t", self.dtype)(
+            _ptr(Lp), Lp.stride(1), Lp.stride(0), self.n_pad, _ptr(Bt), Bt.stride(1), Bt.stride(0), Bt.shape[1],
+            self.batch, _stream(),
+        )
+        check(rc, "gpk_trsm_right_t")
+        return Bt
+
+    def half_solve(self, bt):
+        """``bt [B, m, n]`` (rows = right-hand sides) -> ``(L^-1 b)^T [B, m, n]``."""
+        m = bt.shape[1]
+        buf = self.new_rows(m)
+        buf[:, :m, : self.n] = bt
+        self.solve_rows_(buf)
+        return buf[:, :m, : self.n]
+
+    def full_solve(self, bt):
+        """``bt [B, m, n]`` -> ``(K^-1 b)^T [B, m, n]``."""
+        m = bt.shape[1]
+        buf = self.new_rows(m)
+        buf[:, :m, : self.n] = bt
+        self.solve_rows_(buf)
+        self.solve_rows_t_(buf)
+        return buf[:, :m, : self.n]
+
+
+def _new_workspace(B, n, k, device, dtype, rhs_t):
+    n_pad = round_up(max(n, 1))
+    extra = round_up(k) if k > 0 else 0
+    W = torch.empty(B, n_pad + extra, n_pad, device=device, dtype=dtype)
+    if extra:
+        W[:, n_pad:, :].zero_()
+        W[:, n_pad : n_pad + k, :n] = rhs_t
+    return W, n_pad, extra
+
+
+def _potrf(W, n, n_pad, extra, k):
+    B = W.shape[0]
+    logdet = torch.zeros(B, device=W.device, dtype=W.dtype)
+    info = torch.zeros(B, device=W.device, dtype=torch.int32)
+    rc = _fn("gpk_potrf", W.dtype)(_ptr(W), W.stride(1), W.stride(0), n_pad, extra, _ptr(logdet), _ptr(info), B,
+                                   _stream())
+    check(rc, "gpk_potrf")
+    return Chol(W, n, k, logdet, info)
+
+
+def chol_from_kernel(flat, xg, *, noise_scalar=0.0, noise_vec=None, jitter=0.0, rhs_t=None):
+    """Build ``k(x, x) + noise + jitter I`` straight into the padded lower workspace (K1), factorise it in place
+    (K2) and carry ``rhs_t [B, k, n]`` through the factorisation (fused K3).  Returns a :class:`Chol`."""
+    _check_groups(xg, flat)
+    _require_cuda(xg, noise_vec, rhs_t)
+    B, n, d = xg.shape[1], xg.shape[2], xg.shape[3]
+    k = 0 if rhs_t is None else rhs_t.shape[1]
+    W, n_pad, extra = _new_workspace(B, n, k, xg.device, xg.dtype, rhs_t)
+    _km_launch(flat, xg, xg, n, n, d, KM_LOWER | KM_SAME | KM_PAD_IDENTITY, noise_scalar, noise_vec, jitter, W,
+               W.stride(1), W.stride(0), B)
+    return _potrf(W, n, n_pad, extra, k)
+
+
+def chol_from_dense(K, *, jitter=0.0, rhs_t=None):
+    """Factorise a given dense SPD ``K [B, n, n]`` (+ ``jitter I``); only its lower triangle is used."""
+    _require_cuda(K, rhs_t)
+    if K.stride(2) != 1:
+        K = K.contiguous()
+    B, n = K.shape[0], K.shape[1]
+    k = 0 if rhs_t is None else rhs_t.shape[1]
+    W, n_pad, extra = _new_workspace(B, n, k, K.device, K.dtype, rhs_t)
+    _pad_copy(K, W, n, n, n_pad, n_pad, jitter, True)
+    return _potrf(W, n, n_pad, extra, k)
+
+
+def kernel_rows_padded(flat, xsg, xg, chol):
+    """``k(x*, x)`` as a zero-padded ``[B, m_pad, n_pad]`` buffer (rows = test points) ready for ``solve_rows_``."""
+    _check_groups(xg, flat)
+    B, m, d = xsg.shape[1], xsg.shape[2], xsg.shape[3]
+    n = xg.shape[2]
+    out = torch.empty(B, round_up(max(m, 1)), chol.n_pad, device=xg.device, dtype=xg.dtype)
+    _km_launch(flat, xsg, xg, m, n, d, KM_PAD_ZERO, 0.0, None, 0.0, out, out.stride(1), out.stride(0), B)
+    return out
+
+
+def probe_dmma_tflops():
+    return float(_lib.load().gpk_probe_dmma_tflops())
+
+
+LOG_2_PI = math.log(2 * math.pi)
