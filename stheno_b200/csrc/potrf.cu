@@ -14,6 +14,8 @@
 //
 // Reference arithmetic replaced: B.cholesky / B.logdet / B.solve (stheno/random.py:274-276,
 // stheno/model/observations.py:300-301,334).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gpk {
@@ -39,6 +41,10 @@ constexpr int NB = 128;
 template <typename T>
 __device__ __forceinline__ T t_sqrt_(T v) {
   return sizeof(T) == 8 ? (T)sqrt((double)v) : (T)sqrtf((float)v);
+}
+template <typename T>
+__device__ __forceinline__ T t_rsqrt_(T v) {
+  return sizeof(T) == 8 ? (T)rsqrt((double)v) : (T)rsqrtf((float)v);
 }
 template <typename T>
 __device__ __forceinline__ T t_log_(T v) {
@@ -76,8 +82,10 @@ potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int64_t a_bs, T* __restrict__ 
       __syncthreads();
       const T djj = colbuf[buf][j];
       if (tid == 0 && !(djj > T(0))) atomicCAS(info + bidx, 0, pivot_base + j + 1);
-      const T dsq = t_sqrt_<T>(djj);
-      const T inv = T(1) / dsq;
+      // 1/sqrt via the hardware reciprocal-sqrt seed (+ Newton steps, <= 1 ulp) and sqrt = d * rsqrt(d): takes the
+      // IEEE sqrt + divide software sequences (~350 cycles in fp64) off the per-column critical path.
+      const T inv = t_rsqrt_<T>(djj);
+      const T dsq = djj * inv;
       T li[8], lk[8];
 #pragma unroll
       for (int a = 0; a < 8; ++a) li[a] = colbuf[buf][ti + 16 * a] * inv;
@@ -198,6 +206,123 @@ trsm_leaf_kernel(const T* __restrict__ L, int64_t ldl, int64_t l_bs, T* __restri
   }
 }
 
+// ---- fp64 leaf TRSM on the tensor cores:  X L^T = B  (128 rows per CTA, 16 warps, 8 rows per warp) -------------
+// Rows of a right-side TRSM are independent, so every warp solves its own 8 rows with NO inter-warp
+// synchronisation: the 8 x 128 row block lives in registers as sixteen 8 x 8 DMMA accumulator fragments.  L11 sits in
+// shared memory in the B-operand fragment-major layout of gemm.cu, with each 16 x 16 diagonal block replaced by its
+// inverse.  For each 16-column block jb:   X_jb = A_jb * inv(L_jb,jb)^T ;   A[:, later] -= X_jb * L[later, jb]^T .
+// The accumulator fragment of an 8 x 8 block (lane holds columns 2q, 2q+1 of row lane/4) IS the A-operand fragment
+// pair of the k-permuted DMMA convention used throughout (even-k DMMA takes .x, odd-k DMMA takes .y), so results feed
+// the next product straight from registers.  256 DMMA + 128 LDS.128 per warp; no shared-memory traffic for A at all.
+constexpr int TC_ROWS = 128;
+constexpr int TC_THREADS = 512;
+
+__device__ __forceinline__ int frag_index(int n, int k) {
+  // element (row n, col k) of a 128 x 128 operand in fragment-major layout (16 k8-groups per 8-row block)
+  return (((n >> 3) * 16 + (k >> 3)) * 32 + (n & 7) * 4 + ((k & 7) >> 1)) * 2 + (k & 1);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+trsm_leaf_tc_f64_kernel(const double* __restrict__ L, int64_t ldl, int64_t l_bs, double* __restrict__ B, int64_t ldb,
+                        int64_t b_bs) {
+  extern __shared__ __align__(16) unsigned char tc_smem[];
+  double* Ls = reinterpret_cast<double*>(tc_smem);  // 128 x 128 fragment-major
+  double* Ld = Ls + NB * NB;                         // [8][16][17] diagonal blocks (natural layout)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  L += (int64_t)blockIdx.y * l_bs;
+  B += (int64_t)blockIdx.y * b_bs + (int64_t)blockIdx.x * TC_ROWS * ldb;
+
+  // (1) L11 (lower part, zeros above) -> fragment-major shared memory; 8192 granules of 2 doubles
+  for (int gi = tid; gi < NB * NB / 2; gi += TC_THREADS) {
+    const int c = gi >> 6, g = gi & 63;  // row c, granule g: columns 2g, 2g+1
+    const int k = 2 * g;
+    double2 v = make_double2(0.0, 0.0);
+    if (k <= c) {
+      v = *reinterpret_cast<const double2*>(L + (int64_t)c * ldl + k);
+      if (k + 1 > c) v.y = 0.0;
+    }
+    *reinterpret_cast<double2*>(Ls + frag_index(c, k)) = v;
+    if ((c >> 4) == (k >> 4)) {  // diagonal 16 x 16 block: natural copy for the inversion
+      double* d = Ld + ((c >> 4) * 16 + (c & 15)) * 17 + (k & 15);
+      d[0] = v.x;
+      d[1] = v.y;
+    }
+  }
+  __syncthreads();
+  // (2) invert the eight diagonal blocks: warp d, lane c (< 16) solves L_d x = e_c by forward substitution
+  if (warp < 8 && lane < 16) {
+    const double* Lb = Ld + warp * 16 * 17;
+    double x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      double s = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (k < i) s -= Lb[i * 17 + k] * x[k];
+      x[i] = (i >= lane) ? s / Lb[i * 17 + i] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) Ls[frag_index(warp * 16 + i, warp * 16 + lane)] = x[i];
+  }
+  __syncthreads();
+
+  // (3) this warp's 8 rows as sixteen accumulator fragments
+  double acc[16][2];
+  double* Bw = B + (int64_t)(warp * 8 + (lane >> 2)) * ldb + 2 * (lane & 3);
+#pragma unroll
+  for (int cb = 0; cb < 16; ++cb) {
+    const double2 v = *reinterpret_cast<const double2*>(Bw + cb * 8);
+    acc[cb][0] = v.x;
+    acc[cb][1] = v.y;
+  }
+  const double* Lf = Ls + lane * 2;  // fragment (row block rb, k8 group kg) at Lf + (rb * 16 + kg) * 64
+#pragma unroll
+  for (int jb = 0; jb < 8; ++jb) {
+    double x[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int kg = 0; kg < 2; ++kg) {
+        if (kg > nb) continue;  // the inverse block is lower triangular: its (nb=0, kg=1) 8 x 8 block is zero
+        const double2 b = *reinterpret_cast<const double2*>(Lf + ((2 * jb + nb) * 16 + 2 * jb + kg) * 64);
+        dmma884(x[nb][0], x[nb][1], acc[2 * jb + kg][0], b.x);
+        dmma884(x[nb][0], x[nb][1], acc[2 * jb + kg][1], b.y);
+      }
+    acc[2 * jb][0] = x[0][0];
+    acc[2 * jb][1] = x[0][1];
+    acc[2 * jb + 1][0] = x[1][0];
+    acc[2 * jb + 1][1] = x[1][1];
+    const double nx[2][2] = {{-x[0][0], -x[0][1]}, {-x[1][0], -x[1][1]}};
+#pragma unroll
+    for (int cb = 2 * jb + 2; cb < 16; ++cb)
+#pragma unroll
+      for (int kg = 0; kg < 2; ++kg) {
+        const double2 b = *reinterpret_cast<const double2*>(Lf + (cb * 16 + 2 * jb + kg) * 64);
+        dmma884(acc[cb][0], acc[cb][1], nx[kg][0], b.x);
+        dmma884(acc[cb][0], acc[cb][1], nx[kg][1], b.y);
+      }
+  }
+#pragma unroll
+  for (int cb = 0; cb < 16; ++cb) *reinterpret_cast<double2*>(Bw + cb * 8) = make_double2(acc[cb][0], acc[cb][1]);
+}
+
+static int launch_trsm_leaf_tc_f64(const double* L, int64_t ldl, int64_t l_bs, double* B, int64_t ldb, int64_t b_bs,
+                                   int64_t rows, int32_t batch, cudaStream_t stream) {
+  if (rows == 0) return 0;
+  const int smem = (NB * NB + 8 * 16 * 17) * (int)sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(trsm_leaf_tc_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return -1000 - (int)e;
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(rows / TC_ROWS), (unsigned)batch);
+  trsm_leaf_tc_f64_kernel<<<grid, TC_THREADS, smem, stream>>>(L, ldl, l_bs, B, ldb, b_bs);
+  GPK_COUNT_LAUNCH();
+  GPK_CHECK_LAUNCH();
+  return 0;
+}
+
 template <typename T>
 static int launch_potrf_leaf(T* A, int64_t lda, int64_t a_bs, T* logdet, int32_t* info, int32_t pivot_base,
                              int32_t batch, cudaStream_t stream) {
@@ -226,8 +351,69 @@ static int launch_trsm_leaf(const T* L, int64_t ldl, int64_t l_bs, T* B, int64_t
   return 0;
 }
 
+template <typename T>
+static int trsm_leaf_fwd(const T* L, int64_t ldl, int64_t l_bs, T* B, int64_t ldb, int64_t b_bs, int64_t rows,
+                         int32_t batch, cudaStream_t stream) {
+  return launch_trsm_leaf<T, false>(L, ldl, l_bs, B, ldb, b_bs, rows, batch, stream);
+}
+template <>
+int trsm_leaf_fwd<double>(const double* L, int64_t ldl, int64_t l_bs, double* B, int64_t ldb, int64_t b_bs,
+                          int64_t rows, int32_t batch, cudaStream_t stream) {
+  if (rows % TC_ROWS == 0) return launch_trsm_leaf_tc_f64(L, ldl, l_bs, B, ldb, b_bs, rows, batch, stream);
+  return launch_trsm_leaf<double, false>(L, ldl, l_bs, B, ldb, b_bs, rows, batch, stream);
+}
+
 constexpr int64_t NB_OUTER = 1024;
 
+// Side stream + events for the look-ahead (one set per process; the library is not re-entrant across host threads
+// for potrf, like the reference's global-state model -- SURVEY 8b "Ownership / threading").
+struct Lookahead {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false;
+  Lookahead() {
+    int lo = 0, hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return;
+    if (cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi) != cudaSuccess) return;
+    if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return;
+    if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) return;
+    ok = true;
+  }
+};
+
+static Lookahead& lookahead() {
+  static thread_local Lookahead la;  // thread_local: per host thread, tied to the thread's current device
+  return la;
+}
+
+// Factorise the outer panel [kb, ke): leaf Cholesky, leaf TRSM of all rows below, rank-128 update of the rest of
+// the panel -- for every 128-wide step.
+template <typename T>
+static int factor_panel(T* A, int64_t lda, int64_t a_bs, int64_t R, int64_t kb, int64_t ke, T* logdet, int32_t* info,
+                        int32_t batch, cudaStream_t stream) {
+  int rc;
+  for (int64_t j = kb; j < ke; j += NB) {
+    T* Ajj = A + j * lda + j;
+    if ((rc = launch_potrf_leaf<T>(Ajj, lda, a_bs, logdet, info, (int32_t)j, batch, stream))) return rc;
+    const int64_t below = R - (j + NB);
+    if (below > 0) {
+      T* A21 = A + (j + NB) * lda + j;
+      if ((rc = trsm_leaf_fwd<T>(Ajj, lda, a_bs, A21, lda, a_bs, below, batch, stream))) return rc;
+      const int64_t ncols = ke - (j + NB);
+      if (ncols > 0) {
+        if ((rc = gemm_nt(below, ncols, (int64_t)NB, T(-1), A21, lda, a_bs, A21, lda, a_bs, T(1),
+                          A + (j + NB) * lda + (j + NB), lda, a_bs, 1, batch, stream)))
+          return rc;
+      }
+    }
+  }
+  return 0;
+}
+
+// Right-looking over 1024-wide outer panels WITH LOOK-AHEAD: the trailing update of panel i is split into
+// (a) the columns of panel i+1 and (b) everything to the right of it; as soon as (a) is done the latency-bound
+// factorisation of panel i+1 runs on a high-priority side stream while the tensor-core-bound update (b) keeps the
+// SMs busy on the caller's stream.
 template <typename T>
 static int potrf_driver(T* A, int64_t lda, int64_t a_bs, int64_t n_pad, int64_t extra_rows, T* logdet, int32_t* info,
                         int32_t batch, cudaStream_t stream) {
@@ -236,28 +422,37 @@ static int potrf_driver(T* A, int64_t lda, int64_t a_bs, int64_t n_pad, int64_t 
   if (lda % (16 / sizeof(T)) || reinterpret_cast<uintptr_t>(A) % 16) return GPK_ERR_ALIGN;
   const int64_t R = n_pad + extra_rows;
   int rc;
-  for (int64_t kb = 0; kb < n_pad; kb += NB_OUTER) {
-    const int64_t ke = (kb + NB_OUTER < n_pad) ? kb + NB_OUTER : n_pad;
-    for (int64_t j = kb; j < ke; j += NB) {
-      T* Ajj = A + j * lda + j;
-      if ((rc = launch_potrf_leaf<T>(Ajj, lda, a_bs, logdet, info, (int32_t)j, batch, stream))) return rc;
-      const int64_t below = R - (j + NB);
-      if (below > 0) {
-        T* A21 = A + (j + NB) * lda + j;
-        if ((rc = launch_trsm_leaf<T, false>(Ajj, lda, a_bs, A21, lda, a_bs, below, batch, stream))) return rc;
-        const int64_t ncols = ke - (j + NB);
-        if (ncols > 0) {
-          if ((rc = gemm_nt(below, ncols, (int64_t)NB, T(-1), A21, lda, a_bs, A21, lda, a_bs, T(1),
-                            A + (j + NB) * lda + (j + NB), lda, a_bs, 1, batch, stream)))
-            return rc;
-        }
-      }
+  Lookahead& la = lookahead();
+  const bool use_la = la.ok && n_pad > 2 * NB_OUTER && getenv("GPK_NO_LOOKAHEAD") == nullptr;
+  auto ce = [](cudaError_t e) { return e == cudaSuccess ? 0 : -1000 - (int)e; };
+
+  const int64_t ke0 = NB_OUTER < n_pad ? NB_OUTER : n_pad;
+  if ((rc = factor_panel<T>(A, lda, a_bs, R, 0, ke0, logdet, info, batch, stream))) return rc;
+  for (int64_t kb = 0; kb + NB_OUTER < n_pad; kb += NB_OUTER) {
+    const int64_t ke = kb + NB_OUTER;                                   // panel [kb, ke) is factorised
+    const int64_t ke2 = (ke + NB_OUTER < n_pad) ? ke + NB_OUTER : n_pad;  // next panel [ke, ke2)
+    const int64_t K = ke - kb;
+    // (a) update the next panel's columns
+    if ((rc = gemm_nt(R - ke, ke2 - ke, K, T(-1), A + ke * lda + kb, lda, a_bs, A + ke * lda + kb, lda, a_bs, T(1),
+                      A + ke * lda + ke, lda, a_bs, 1, batch, stream)))
+      return rc;
+    const bool more = ke2 < n_pad;
+    if (use_la && more) {
+      if ((rc = ce(cudaEventRecord(la.fork, stream)))) return rc;
+      if ((rc = ce(cudaStreamWaitEvent(la.side, la.fork, 0)))) return rc;
+      if ((rc = factor_panel<T>(A, lda, a_bs, R, ke, ke2, logdet, info, batch, la.side))) return rc;
+      if ((rc = ce(cudaEventRecord(la.join, la.side)))) return rc;
     }
-    if (ke < n_pad) {
-      const T* P = A + ke * lda + kb;
-      if ((rc = gemm_nt(R - ke, n_pad - ke, ke - kb, T(-1), P, lda, a_bs, P, lda, a_bs, T(1), A + ke * lda + ke, lda,
-                        a_bs, 1, batch, stream)))
+    // (b) update everything to the right of the next panel
+    if (more) {
+      if ((rc = gemm_nt(R - ke2, n_pad - ke2, K, T(-1), A + ke2 * lda + kb, lda, a_bs, A + ke2 * lda + kb, lda, a_bs,
+                        T(1), A + ke2 * lda + ke2, lda, a_bs, 1, batch, stream)))
         return rc;
+    }
+    if (use_la && more) {
+      if ((rc = ce(cudaStreamWaitEvent(stream, la.join, 0)))) return rc;
+    } else {
+      if ((rc = factor_panel<T>(A, lda, a_bs, R, ke, ke2, logdet, info, batch, stream))) return rc;
     }
   }
   return 0;
@@ -268,7 +463,7 @@ template <typename T>
 static int trsm_right_rec(const T* L, int64_t ldl, int64_t l_bs, int64_t n, T* B, int64_t ldb, int64_t b_bs,
                           int64_t rows, int32_t batch, cudaStream_t stream) {
   if (n <= 0) return 0;
-  if (n == NB) return launch_trsm_leaf<T, false>(L, ldl, l_bs, B, ldb, b_bs, rows, batch, stream);
+  if (n == NB) return trsm_leaf_fwd<T>(L, ldl, l_bs, B, ldb, b_bs, rows, batch, stream);
   const int64_t h = ((n / NB) / 2) * NB;
   int rc;
   if ((rc = trsm_right_rec<T>(L, ldl, l_bs, h, B, ldb, b_bs, rows, batch, stream))) return rc;

@@ -52,15 +52,18 @@ class Input:
 
     def scaled(self, scales):
         """``[G, B, n, d]``: one pre-stretched copy of the points per distinct length scale (``x / scale``)."""
-        key = tuple(id(s) if isinstance(s, torch.Tensor) else s for s in scales)
+        key = tuple(_scale_key(s) for s in scales)
         if key not in self._groups:
             t3, _ = batch_flatten(self.t, 2)
             parts = []
             for s in scales:
                 if s is None:
                     parts.append(t3)
+                elif isinstance(s, torch.Tensor):
+                    parts.append(t3 / s.to(device=t3.device, dtype=t3.dtype))
                 else:
-                    parts.append(t3 / (s if isinstance(s, torch.Tensor) else float(s)))
+                    a = np.asarray(s, np.float64)
+                    parts.append(t3 / (float(a) if a.ndim == 0 else torch.as_tensor(a, dtype=t3.dtype, device=t3.device)))
             self._groups[key] = torch.stack(parts).contiguous()
         return self._groups[key]
 
@@ -544,10 +547,10 @@ def _paren(k):
 # ------------------------------------------------------------------------------------------------------------
 def pairwise(k, x, y=None):
     """``k(x, y)`` -> structured matrix.  ``y=None`` (or ``y is x``) means the same object."""
-    from .mo.kernel import MultiOutputKernel, mo_pairwise
+    from .mo.kernel import mo_pairwise
 
     same = y is None or y is x
-    if isinstance(k, MultiOutputKernel) or _is_multi(x) or (not same and _is_multi(y)):
+    if hasattr(k, "_pairwise_multi") or _is_multi(x) or (not same and _is_multi(y)):
         return mo_pairwise(k, x, x if same else y, same)
     xi = as_input(x)
     yi = xi if same else as_input(y)
@@ -555,19 +558,13 @@ def pairwise(k, x, y=None):
 
 
 def elwise_dev(k, x, y, same):
-    return k._elwise_dev(x, x if same else y, same)
+    return _elwise_any(k, x, None if same else y, same)
 
 
 def elwise(k, x, y=None):
     """``k.elwise(x, y)`` -> column ``(n, 1)`` in the caller's array type."""
-    from .mo.kernel import MultiOutputKernel, mo_elwise
-
     same = y is None or y is x
-    if isinstance(k, MultiOutputKernel) or _is_multi(x) or (not same and _is_multi(y)):
-        return mo_elwise(k, x, x if same else y, same)
-    xi = as_input(x)
-    yi = xi if same else as_input(y)
-    return from_dev(k._elwise_dev(xi, yi, same), xi.origin)
+    return from_dev(_elwise_any(k, x, None if same else y, same), _origin_of_input(x))
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -575,11 +572,11 @@ def elwise(k, x, y=None):
 # ------------------------------------------------------------------------------------------------------------
 def _cross_rows(k_zi, z, x, ch):
     """``k_zi(z, x)^T`` as a zero-padded ``[B, m_pad, n_pad]`` row buffer (rows = points of ``x``)."""
-    flat, scales = k_zi._flat() if k_zi.symmetric else (None, None)
-    xi, zi = as_input(x), as_input(z)
-    m, n = xi.n, zi.n
-    if flat is not None and flat.terms and not _is_multi(x) and not _is_multi(z):
-        return ops.kernel_rows_padded(flat, xi.scaled(scales), zi.scaled(scales), ch), m
+    if not _is_multi(x) and not _is_multi(z) and k_zi.symmetric:
+        flat, scales = k_zi._flat()
+        if flat is not None and flat.terms:
+            xi, zi = as_input(x), as_input(z)
+            return ops.kernel_rows_padded(flat, xi.scaled(scales), zi.scaled(scales), ch), xi.n
     Kzx = M.dense(pairwise(k_zi, z, x))  # [..., n, m]
     K3, _ = batch_flatten(Kzx, 2)
     buf = ch.new_rows(K3.shape[2])
@@ -706,10 +703,10 @@ def _batch_shape_of_input(x):
 
 
 def _elwise_any(k, x, y, same):
-    """Device column for any input kind."""
-    from .mo.kernel import MultiOutputKernel, mo_elwise_dev
+    """Device column ``[..., n, 1]`` of ``k.elwise(x, y)`` for any input kind."""
+    from .mo.kernel import mo_elwise_dev
 
-    if isinstance(k, MultiOutputKernel) or _is_multi(x) or (not same and _is_multi(y)):
+    if hasattr(k, "_elwise_multi") or _is_multi(x) or (not same and _is_multi(y)):
         return mo_elwise_dev(k, x, x if same else y, same)
     xi = as_input(x)
     return k._elwise_dev(xi, xi if same else as_input(y), same)
@@ -720,19 +717,16 @@ def _elwise_any(k, x, y, same):
 # ------------------------------------------------------------------------------------------------------------
 class Mean:
     def __call__(self, x):
-        from .mo.kernel import MultiOutputMean, mo_mean
-
-        if isinstance(self, MultiOutputMean) or _is_multi(x):
-            return mo_mean(self, x)
-        xi = as_input(x)
-        return from_dev(self._dev(xi), xi.origin)
+        return from_dev(self.dev(x), _origin_of_input(x))
 
     def dev(self, x):
-        """Device column ``[..., n, 1]`` for any input kind."""
-        from .mo.kernel import MultiOutputMean, mo_mean_dev
+        """Device column ``[..., n, 1]`` for any input kind (numeric, FDD, tuple)."""
+        from .model.fdd import FDD
 
-        if isinstance(self, MultiOutputMean) or _is_multi(x):
-            return mo_mean_dev(self, x)
+        if isinstance(x, tuple):
+            return torch.cat([self.dev(xi) for xi in x], dim=-2)
+        if isinstance(x, FDD):
+            raise ValueError(f"{type(self).__name__} cannot be evaluated at an FDD")
         return self._dev(as_input(x))
 
     def _dev(self, x):
@@ -816,8 +810,8 @@ class ScaledMean(Mean):
     def __init__(self, m, scale):
         self.m, self.scale = m, scale
 
-    def _dev(self, x):
-        return self.scale * self.m._dev(x)
+    def dev(self, x):
+        return self.scale * self.m.dev(x)
 
     def render(self):
         return f"{_fmt(self.scale)} * {self.m.render()}"
@@ -827,8 +821,8 @@ class SumMean(Mean):
     def __init__(self, a, b):
         self.a, self.b = a, b
 
-    def _dev(self, x):
-        return self.a._dev(x) + self.b._dev(x)
+    def dev(self, x):
+        return self.a.dev(x) + self.b.dev(x)
 
     def render(self):
         return f"{self.a.render()} + {self.b.render()}"
@@ -838,8 +832,8 @@ class ProductMean(Mean):
     def __init__(self, a, b):
         self.a, self.b = a, b
 
-    def _dev(self, x):
-        return self.a._dev(x) * self.b._dev(x)
+    def dev(self, x):
+        return self.a.dev(x) * self.b.dev(x)
 
     def render(self):
         return f"{self.a.render()} * {self.b.render()}"
@@ -909,14 +903,8 @@ class PosteriorMean(Mean):
         prior = self.m_i.dev(x)
         return prior + dot.reshape(prior.shape[:-1]).unsqueeze(-1)
 
-    def _dev(self, x):
-        return self._dev_any(x)
-
     def dev(self, x):
         return self._dev_any(x)
-
-    def __call__(self, x):
-        return from_dev(self._dev_any(x), _origin_of_input(x))
 
     def render(self):
         return "PosteriorMean()"

@@ -1,0 +1,148 @@
+"""``GP``: a handle into a :class:`Measure` (``stheno/model/gp.py:58-274``; hot-path subset: construction,
+``f(x, noise)``, conditioning, ``+``, ``* scalar``, ``stretch``)."""
+from types import FunctionType
+
+import numpy as np
+import torch
+
+from ..kernels import Kernel, Mean, OneKernel, OneMean, ZeroMean, FunctionMean
+from ..random import RandomProcess
+from .fdd import FDD
+
+__all__ = ["assert_same_measure", "intersection_measure_group", "cross", "GP"]
+
+
+def assert_same_measure(*ps):
+    for p in ps[1:]:
+        if ps[0].measure != p.measure:
+            raise AssertionError(f"Processes {ps[0]} and {p} are associated to different measures.")
+
+
+def intersection_measure_group(*ps):
+    assert_same_measure(*ps)
+    inter = list(ps[0]._measures)
+    for p in ps[1:]:
+        inter = [m for m in inter if any(m is q for q in p._measures)]
+    return inter
+
+
+def cross(*ps):
+    """Cartesian product of processes: a multi-output GP (``gp.py:43-55``)."""
+    p_cross = GP()
+    for measure in intersection_measure_group(*ps):
+        measure.cross(p_cross, *ps)
+    return p_cross
+
+
+def _is_numeric(v):
+    return isinstance(v, (int, float, np.number, np.ndarray, torch.Tensor))
+
+
+class GP(RandomProcess):
+    """``GP([mean,] kernel, *, measure=None, name=None)``; ``GP()`` makes an unattached handle."""
+
+    def __init__(self, *args, measure=None, name=None):
+        self._measures = []
+        if len(args) == 0:
+            return
+        from .measure import Measure
+
+        if len(args) == 1:
+            mean, kernel = ZeroMean(), args[0]
+        elif len(args) == 2:
+            mean, kernel = args
+        else:
+            raise TypeError("GP([mean,] kernel)")
+        if measure is None:
+            measure = Measure.default if Measure.default is not None else Measure()
+        if isinstance(mean, FunctionType):
+            mean = FunctionMean(mean)
+        elif _is_numeric(mean):
+            mean = mean * OneMean()
+        if isinstance(kernel, FunctionType):
+            raise NotImplementedError("function-valued kernels are outside the hot-path scope")
+        if _is_numeric(kernel):
+            kernel = kernel * OneKernel()
+        measure.add_independent_gp(self, mean, kernel)
+        if name:
+            measure.name(self, name)
+
+    @property
+    def measure(self):
+        if len(self._measures) == 0:
+            raise RuntimeError("GP is not associated to a measure.")
+        return self._measures[0]
+
+    @property
+    def kernel(self):
+        return self.measure.kernels[self]
+
+    @property
+    def mean(self):
+        return self.measure.means[self]
+
+    @property
+    def name(self):
+        return self.measure[self]
+
+    @name.setter
+    def name(self, name):
+        for measure in self._measures:
+            measure.name(self, name)
+
+    def __call__(self, x, noise=None):
+        """``f(x, noise)`` -> :class:`FDD` (``gp.py:134-144``)."""
+        return FDD(self, x, noise)
+
+    def condition(self, *args):
+        posterior = self.measure.condition(*args)
+        return posterior(self)
+
+    def __or__(self, args):
+        """``f | (f(x), y)``, ``f | ((f1(x1), y1), (f2(x2), y2))``, ``f | Obs(...)`` (``gp.py:146-160``)."""
+        if isinstance(args, tuple):
+            return self.condition(*args)
+        return self.condition(args)
+
+    def __add__(self, other):
+        res = GP()
+        if isinstance(other, GP):
+            for measure in intersection_measure_group(self, other):
+                measure.sum(res, self, other)
+        else:
+            for measure in self._measures:
+                measure.sum(res, self, other)
+        return res
+
+    def __mul__(self, other):
+        res = GP()
+        if isinstance(other, GP):
+            raise NotImplementedError("GP * GP (moment matching) is outside the hot-path scope (SURVEY 8f.3)")
+        for measure in self._measures:
+            measure.mul(res, self, other)
+        return res
+
+    def stretch(self, stretch):
+        res = GP()
+        for measure in self._measures:
+            measure.stretch(res, self, stretch)
+        return res
+
+    def _out_of_scope(self, *a, **k):
+        raise NotImplementedError("outside the GP-inference hot-path scope (SURVEY.md 8f rank 3)")
+
+    shift = transform = select = diff = diff_approx = _out_of_scope
+
+    @property
+    def stationary(self):
+        return self.kernel.stationary
+
+    def display(self, formatter=lambda v: v):
+        if self._measures:
+            return f"GP({self.mean.display(formatter)}, {self.kernel.display(formatter)})"
+        return "GP()"
+
+    def __str__(self):
+        return self.display()
+
+    __repr__ = __str__

@@ -1,0 +1,262 @@
+"""Conditioning: exact ``Observations`` and the sparse ``PseudoObservations`` family
+(``stheno/model/observations.py:28-414``)."""
+import numpy as np
+import torch
+
+from .. import B
+from .. import matrix as M
+from .. import ops
+from ..kernels import (PosteriorKernel, PosteriorMean, SubspaceKernel, _cross_rows, _elwise_any, num_elements,
+                       pairwise)
+from .._util import batch_flatten, from_dev, to_dev, uprank
+from .fdd import FDD, _input_meta
+from .gp import cross
+
+__all__ = [
+    "combine", "AbstractObservations", "AbstractPseudoObservations", "Observations", "Obs", "PseudoObservations",
+    "SparseObservations", "PseudoObs", "SparseObs", "PseudoObservationsFITC", "PseudoObsFITC",
+    "PseudoObservationsDTC", "PseudoObsDTC",
+]
+
+
+def combine(*args):
+    """Combine FDDs -- or ``(fdd, y)`` pairs -- into one joint FDD (and stacked ``y``) (``observations.py:28-47``)."""
+    if all(isinstance(a, FDD) for a in args):
+        fdds = args
+        combined_noise = M.block_diag(*[fdd.noise for fdd in fdds])
+        return cross(*[fdd.p for fdd in fdds])(tuple(fdds), combined_noise)
+    fdds, ys = zip(*args)
+    combined_fdd = combine(*fdds)
+    dtype = _input_meta(combined_fdd.x)[0]
+    combined_y = torch.cat([uprank(to_dev(y, dtype)) for y in ys], dim=-2)
+    return combined_fdd, combined_y
+
+
+class AbstractObservations:
+    def __init__(self, *args):
+        if len(args) == 2 and isinstance(args[0], FDD):
+            fdd, y = args
+        else:
+            fdd, y = combine(*args)
+        y_shape = tuple(np.shape(y)) if not isinstance(y, torch.Tensor) else tuple(y.shape)
+        y = uprank(to_dev(y, _input_meta(fdd.x)[0]))
+        if y.shape[-1] != 1:
+            raise ValueError(f"Invalid shape of observed values {y_shape}.")
+        # Missing data: one device reduction + flag; the gather path only runs when NaNs exist.
+        nan = torch.isnan(y[..., :, 0])
+        if bool(nan.any()):
+            avail = ~nan
+            fdd = fdd.take(avail)
+            y = y[avail]
+        self.fdd = fdd
+        self.y = y
+
+    def posterior_kernel(self, measure, p_i, p_j):  # pragma: no cover
+        raise NotImplementedError("Posterior kernel construction not implemented.")
+
+    def posterior_mean(self, measure, p):  # pragma: no cover
+        raise NotImplementedError("Posterior mean construction not implemented.")
+
+
+class Observations(AbstractObservations):
+    """Exact observations ``(f(x, noise), y)``.  The factor of ``K_x`` is computed once per measure and reused by
+    every prediction (``observations.py:127-141``); ``L^-1 (y - m(x))`` rides along in that factorisation."""
+
+    def __init__(self, *args):
+        AbstractObservations.__init__(self, *args)
+        self._K_x = {}
+
+    def K_x(self, measure):
+        try:
+            return self._K_x[id(measure)]
+        except KeyError:
+            K_x = M.add(pairwise(measure.kernels[self.fdd.p], self.fdd.x), self.fdd.noise)
+            if isinstance(K_x, M.Dense):
+                diff = self.y - measure.means[self.fdd.p].dev(self.fdd.x)
+                d3, _ = batch_flatten(diff, 2)
+                K_x.attach_rhs(("obs", id(self)), d3.transpose(1, 2).contiguous())
+            self._K_x[id(measure)] = K_x
+            return K_x
+
+    def posterior_kernel(self, measure, p_i, p_j):
+        if num_elements(self.fdd.x) == 0:
+            return measure.kernels[p_i, p_j]
+        return PosteriorKernel(
+            measure.kernels[p_i, p_j],
+            measure.kernels[self.fdd.p, p_i],
+            measure.kernels[self.fdd.p, p_j],
+            self.fdd.x,
+            self.K_x(measure),
+        )
+
+    def posterior_mean(self, measure, p):
+        if num_elements(self.fdd.x) == 0:
+            return measure.means[p]
+        return PosteriorMean(
+            measure.means[p],
+            measure.means[self.fdd.p],
+            measure.kernels[self.fdd.p, p],
+            self.fdd.x,
+            self.K_x(measure),
+            self.y,
+            rhs_key=("obs", id(self)),
+        )
+
+
+class AbstractPseudoObservations(AbstractObservations):
+    """Observations through inducing points ``u`` (VFE / FITC / DTC), ``observations.py:171-336``."""
+
+    method = None
+
+    def __init__(self, u, *args):
+        AbstractObservations.__init__(self, *args)
+        if isinstance(u, tuple):
+            u = combine(*u)
+        self.u = u
+        self._K_z, self._elbo, self._mu, self._A = {}, {}, {}, {}
+
+    def _get(self, store, measure):
+        try:
+            return store[id(measure)]
+        except KeyError:
+            self._compute(measure)
+            return store[id(measure)]
+
+    def K_z(self, measure):
+        return self._get(self._K_z, measure)
+
+    def elbo(self, measure):
+        e = self._get(self._elbo, measure)
+        return from_dev(e, _input_meta(self.fdd.x)[2])
+
+    def mu(self, measure):
+        return self._get(self._mu, measure)
+
+    def A(self, measure):
+        return self._get(self._A, measure)
+
+    def posterior_kernel(self, measure, p_i, p_j):
+        return PosteriorKernel(
+            measure.kernels[p_i, p_j],
+            measure.kernels[self.u.p, p_i],
+            measure.kernels[self.u.p, p_j],
+            self.u.x,
+            self.K_z(measure),
+        ) + SubspaceKernel(
+            measure.kernels[self.u.p, p_i],
+            measure.kernels[self.u.p, p_j],
+            self.u.x,
+            self.A(measure),
+        )
+
+    def posterior_mean(self, measure, p):
+        return PosteriorMean(
+            measure.means[p],
+            measure.means[self.u.p],
+            measure.kernels[self.u.p, p],
+            self.u.x,
+            self.K_z(measure),
+            self.mu(measure),
+        )
+
+    def _compute(self, measure):
+        """``observations.py:279-336`` with ``W^T = K_xz L_z^-T`` kept in row form ``[n, m]`` (rows = data points):
+        the m^2 n flops of the solve and of ``A = I + W K_n^-1 W^T`` both run on the tensor-core GEMM."""
+        p_x, x, noise_x = self.fdd.p, self.fdd.x, self.fdd.noise
+        p_z, z, noise_z = self.u.p, self.u.x, self.u.noise
+        K_z = M.add(pairwise(measure.kernels[p_z], z), noise_z)  # :286
+        self._K_z[id(measure)] = K_z
+        K_n = noise_x  # :290
+        if not isinstance(K_n, M.Diagonal):
+            raise RuntimeError(
+                f'Kernel matrix of observation noise must be diagonal, not "{type(K_n).__name__}".'
+            )
+        K_z = M.as_matrix(K_z)
+        ch_z = K_z.chol()  # :300
+        m, m_pad = ch_z.n, ch_z.n_pad
+        # :285 + :301  W^T = (L_z^-1 K_zx)^T, rows = data points, zero padded [B, n_pad, m_pad]
+        Wt, n = _cross_rows(measure.kernels[p_z, p_x], z, x, ch_z)
+        ch_z.solve_rows_(Wt)
+        kn = K_n.diag
+        kn3 = kn.reshape(-1, kn.shape[-1])
+        if kn3.shape[0] != ch_z.batch:
+            kn3 = kn3.expand(ch_z.batch, -1)
+        if self.method in ("vfe", "fitc"):
+            K_x_diag = _elwise_any(measure.kernels[p_x], x, None, True)[..., 0]  # :304
+            _, Q_x_diag = ops.row_dot_sq(Wt, n, m_pad, None)  # :305
+            corr = K_x_diag.reshape(ch_z.batch, n) - Q_x_diag  # :306
+        if self.method == "vfe":
+            trace_part = (corr / kn3).sum(-1)  # :308-310
+        elif self.method == "fitc":
+            kn3 = kn3 + corr  # :311-313
+            trace_part = 0.0
+        elif self.method == "dtc":
+            trace_part = 0.0
+        else:  # pragma: no cover
+            raise ValueError(f'Invalid approximation method "{self.method}".')
+        # A = I + W K_n^-1 W^T  (:322): scale the rows by K_n^-1/2 (in place: W itself is no longer needed),
+        # transpose to the K-contiguous form the tensor-core GEMM wants, SYRK on the lower tiles.
+        n_pad = Wt.shape[1]
+        rs = torch.rsqrt(kn3)
+        Wt[:, :n] *= rs.unsqueeze(-1)
+        WsT = torch.empty(ch_z.batch, m_pad, n_pad, dtype=Wt.dtype, device=Wt.device)
+        ops.transpose(Wt, n_pad, m_pad, out=WsT)  # [B, m_pad, n_pad]
+        del Wt
+        A = torch.zeros(ch_z.batch, m_pad, m_pad, dtype=WsT.dtype, device=WsT.device)
+        A.diagonal(dim1=1, dim2=2).fill_(1.0)
+        ops.gemm_nt(WsT, WsT, A, alpha=1.0, beta=1.0, lower=True)
+        ops.symmetrize_(A, m_pad)
+        A_mat = M.Dense(A[:, :m, :m])
+        # optimal mean (:326-329)
+        mean_z = measure.means[p_z].dev(z)
+        y_bar = uprank(self.y) - measure.means[p_x].dev(x)
+        yb3, _ = batch_flatten(y_bar, 2)  # [B, n, 1]
+        ybs = torch.zeros(ch_z.batch, n_pad, dtype=WsT.dtype, device=WsT.device)
+        ybs[:, :n] = yb3[..., 0] * rs
+        prod, _ = ops.row_dot_sq(WsT, m, n_pad, ybs, want_sq=False)  # [B, m] = W K_n^-1 y_bar  (:327)
+        del WsT
+        ch_A = A_mat.chol()
+        half = ch_A.half_solve(prod.unsqueeze(1))  # [B, 1, m]  L_A^-1 prod
+        sol = ch_A.full_solve(prod.unsqueeze(1))  # A^-1 prod
+        Lz_pad = torch.tril(ch_z.L_padded())  # zero strict upper triangle; identity on the padding
+        solp = torch.zeros(ch_z.batch, ops.TILE, m_pad, dtype=A.dtype, device=A.device)
+        solp[:, :1, :m] = sol
+        mu_rows = ops.gemm_nt(solp, Lz_pad)  # row 0 = (L_z A^-1 prod)^T
+        mu = mean_z + mu_rows[:, 0, :m].reshape(mean_z.shape[:-1]).unsqueeze(-1)  # :329
+        self._mu[id(measure)] = mu
+        # stored "A" = L_z A L_z^T (:323) as two NT products (A is symmetric)
+        U = ops.gemm_nt(Lz_pad, A)
+        LAL = ops.gemm_nt(U, Lz_pad)
+        self._A[id(measure)] = M.Dense(LAL[:, :m, :m].reshape(K_z.shape), K_z.origin)
+        # ELBO (:333-336)
+        det_part = torch.log(2 * B.pi * kn3).sum(-1) + ch_A.logdet
+        iqf_part = (yb3[..., 0] ** 2 / kn3).sum(-1) - (half * half).sum((-1, -2))
+        elbo = -0.5 * (det_part + iqf_part + trace_part)
+        bs = K_z.shape[:-2]
+        self._elbo[id(measure)] = elbo.reshape(bs) if bs else elbo[0]
+
+
+class PseudoObservations(AbstractPseudoObservations):
+    """VFE (Titsias, 2009)."""
+
+    method = "vfe"
+
+
+class PseudoObservationsFITC(AbstractPseudoObservations):
+    """FITC (Snelson & Ghahramani, 2006)."""
+
+    method = "fitc"
+
+
+class PseudoObservationsDTC(AbstractPseudoObservations):
+    """DTC (Csato & Opper, 2002; Seeger et al., 2003)."""
+
+    method = "dtc"
+
+
+Obs = Observations
+PseudoObs = PseudoObservations
+PseudoObsFITC = PseudoObservationsFITC
+PseudoObsDTC = PseudoObservationsDTC
+SparseObs = PseudoObservations
+SparseObservations = PseudoObservations

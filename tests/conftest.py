@@ -25,3 +25,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def cpu_backend(monkeypatch):
+    """Host-logic tests: run the model layer on torch-CPU stand-ins of the CUDA ops (tests/_cpu_backend.py)."""
+    from tests import _cpu_backend
+
+    _cpu_backend.install(monkeypatch)
+    return _cpu_backend
