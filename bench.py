@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- log-marginal-likelihoods/sec of the GP hot path (BASELINE.json metric).
+
+Workload at N=1 (``config.workload``): BASELINE.json configs[1] -- ``EQ().stretch(l) + s2*Delta()``, n=16384, d=8,
+fp64, one logpdf = fused kernel-matrix build -> Cholesky (+ fused triangular solve, log-det) -> finish.
+Synthetic inputs: x ~ N(0,1)^{n x d}, l = 2.0, s2 = 0.1, y ~ N(0,1)^n, seed = 2 + rank.
+
+A "step" is one logpdf evaluation through the public API (``GP(k)(x, noise).logpdf(y)``).
+  value  : steps/s with x, y already resident in HBM (CUDA-event timed, max over ranks)
+  e2e    : the same call with HOST (pinned) x, y: H2D of the inputs and D2H of the scalar inside the timed region
+  roofline: in-situ event timing of the dominant kernel (fp64 tensor-core GEMM) vs the DMMA peak measured in-run
+  cpu_baseline: the NumPy/SciPy oracle (the reference cannot be imported here) on the host cores, bounded sample
+N > 1 (torchrun): "replicas only" -- a single dense Cholesky does not shard; every rank evaluates its own
+independent problem (e.g. a hyper-parameter sweep), no data-path collective; value = N*K / max-rank time.
+
+``--impl reference`` times the oracle port of the reference's CPU path on the box's host cores (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FULL, D, ELL, S2 = 16384, 8, 2.0, 0.1
+METRIC = "log-marginal-likelihoods/sec (n=16384 fp64 EQ)"
+UNIT = "logpdf/s"
+
+
+def make_inputs(seed, n=N_FULL):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, D))
+    y = rng.standard_normal(n)
+    return x, y
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement of the reference's numpy path
+# ----------------------------------------------------------------------------------------------------------------------
+def oracle_logpdf(x, y):
+    from oracle import gp_oracle as O
+
+    spec = ("sum", ("stretched", ELL, ("eq",)), ("scaled", S2, ("delta",)))
+    return float(O.fdd_logpdf(spec, x, None, y))
+
+
+def cpu_threads():
+    try:
+        import threadpoolctl
+
+        ts = [d.get("num_threads", 1) for d in threadpoolctl.threadpool_info() if d.get("user_api") == "blas"]
+        return max(ts) if ts else (os.cpu_count() or 1)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cost(n):
+    """Algorithmic flops of one logpdf: n^3/3 + n^2 k + n^2 (3d + 8)."""
+    return n**3 / 3.0 + n * n + n * n * (3 * D + 8)
+
+
+def time_oracle(n, reps=1):
+    x, y = make_inputs(2, n)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        oracle_logpdf(x, y)
+        ts.append(time.perf_counter() - t0)
+    return min(ts)
+
+
+def pick_sample_n(budget_s):
+    """Largest n in {16384, 8192, 4096, 2048} whose predicted oracle time fits the per-step budget."""
+    t2k = time_oracle(2048, reps=2)  # also warms BLAS up
+    for n in (16384, 8192, 4096, 2048):
+        pred = t2k * (0.5 * cost(n) / cost(2048) + 0.5 * (n / 2048.0) ** 2)  # mix of n^3 (BLAS-3) and n^2 (build)
+        if pred <= budget_s:
+            return n
+    return 2048
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    total_budget = 150.0
+    n_s = pick_sample_n(total_budget / (args.steps + args.warmup))
+    x, y = make_inputs(2, n_s)
+    for _ in range(args.warmup):
+        oracle_logpdf(x, y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_logpdf(x, y)
+    dt = (time.perf_counter() - t0) / args.steps
+    scale = cost(N_FULL) / cost(n_s)
+    value = 1.0 / (dt * scale)
+    sample = (f"{args.steps} x oracle logpdf at n={n_s}, d={D} ({dt:.3f} s each)"
+              + ("" if n_s == N_FULL else f", scaled to n={N_FULL} by the algorithmic flop ratio {scale:.1f}"))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "EQ().stretch(2.0)+0.1*Delta(), n=16384, d=8, fp64: kernel build + Cholesky + logpdf",
+                   "parallelism": "host cores (numpy/scipy oracle restatement of the reference path)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gpu_arm(args, rank, world, local_rank):
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device -- the GPU arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import stheno_b200 as S
+    from stheno_b200 import ops
+
+    S.B.epsilon = 1e-12
+    dev = torch.device("cuda", local_rank)
+    x_np, y_np = make_inputs(2 + rank)
+    x_dev = torch.as_tensor(x_np, device=dev)
+    y_dev = torch.as_tensor(y_np, device=dev)
+    x_host = torch.as_tensor(x_np).pin_memory()
+    y_host = torch.as_tensor(y_np).pin_memory()
+    kernel = S.EQ().stretch(ELL) + S2 * S.Delta()
+
+    def step_resident():
+        return S.GP(kernel)(x_dev, None).logpdf(y_dev)
+
+    def step_e2e():
+        # public API with HOST buffers: inputs are copied H2D, the scalar result comes back D2H (numpy-like usage)
+        lp = S.GP(kernel)(x_host, None).logpdf(y_host)
+        return float(lp)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms, out, (t0, t1)
+
+    for _ in range(max(args.warmup, 3)):
+        lp = step_resident()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    ops.launch_count(reset=True)
+    ms, lp, (t0, t1) = timed(step_resident, args.steps)
+    launches = ops.launch_count(reset=True)
+    clocks = sampler.stop(t0, t1)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    value = world * args.steps / (ms * 1e-3)
+    e2e_value = world * args.steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        # roofline leg: dominant kernel = fp64 tensor-core GEMM, timed in situ with events on its own stream
+        # (look-ahead off for these steps: with it on, GEMM launches share the SMs with the side-stream panel
+        # kernels and their event-bracketed durations overlap, which would not be a per-kernel figure)
+        prof_steps = min(args.steps, 3)
+        os.environ["GPK_NO_LOOKAHEAD"] = "1"
+        ops.gemm_profile(True)
+        for _ in range(prof_steps):
+            step_resident()
+        g_ms, g_flops, g_launches = ops.gemm_profile_read()
+        ops.gemm_profile(False)
+        del os.environ["GPK_NO_LOOKAHEAD"]
+        peak = ops.probe_dmma_tflops()
+        achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else None
+        roofline = {
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": (achieved / peak) if achieved and peak > 0 else None, "traffic": None,
+            "kernel": "gpk::gemm_nt_f64_kernel (DMMA.8x8x4)",
+            "peak_source": "fp64 DMMA issue peak measured in-run (gpk_probe_dmma_tflops); MEASURED_PEAKS.json has no fp64 entry",
+            "launches_per_step": g_launches / prof_steps, "kernel_ms_per_step": g_ms / prof_steps,
+            "whole_step_tflops": cost(N_FULL) / (ms / args.steps * 1e-3) / 1e12,
+        }
+        # parity spot check against the oracle on a small instance of the same model (full-size parity: tests/)
+        xs, ys = make_inputs(99, 1024)
+        lp_small = float(S.GP(kernel)(torch.as_tensor(xs, device=dev), None).logpdf(torch.as_tensor(ys, device=dev)))
+        ref_small = oracle_logpdf(xs, ys)
+        # bounded CPU baseline sample: the oracle at the largest n that fits ~25 s
+        n_s = pick_sample_n(25.0)
+        dt = time_oracle(n_s)
+        scale = cost(N_FULL) / cost(n_s)
+        cpu_baseline = {
+            "value": 1.0 / (dt * scale), "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+            "sample": f"1 x oracle logpdf at n={n_s}, d={D} ({dt:.2f} s)"
+                      + ("" if n_s == N_FULL else f", scaled to n={N_FULL} by the algorithmic flop ratio {scale:.1f}"),
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "EQ().stretch(2.0)+0.1*Delta(), n=16384, d=8, fp64: kernel build + Cholesky + logpdf",
+                       "parallelism": "single GPU" if world == 1 else f"replicas only x{world} (independent problems, no data-path collective)",
+                       "l2": "working set 2.1 GB per step >> 126 MB L2 (no flush needed)", "n": N_FULL, "d": D},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 8 + y_host.numel() * 8),
+                    "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "logpdf": float(lp),
+            "parity_small": {"n": 1024, "gpu": lp_small, "oracle": ref_small,
+                             "rel_err": abs(lp_small - ref_small) / abs(ref_small)},
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -174,6 +174,13 @@ int gpk_transpose_f32(const float* src, int64_t lds, int64_t s_bstride, int64_t 
  * achieved TFLOP/s -- the denominator of the fp64 roofline -- or a negative error code.  Synchronises the device. */
 double gpk_probe_dmma_tflops(void);
 
+/* In-situ timing of the dominant kernel (the fp64 tensor-core GEMM) for bench.py's roofline leg: while enabled every
+ * launch is bracketed by CUDA events on its own stream; read() (after the caller synchronised the device) returns the
+ * summed durations, the summed ALGORITHMIC flops (2*128*128*K per computed tile) and the launch count.
+ * enable(0/1) also clears the record. */
+void gpk_gemm_profile_enable(int32_t on);
+int gpk_gemm_profile_read(double* total_ms_host, double* total_flops_host, int64_t* launches_host);
+
 /* Number of kernels this library has launched since load / the last reset (bench.py's `gpu_launches`). */
 int64_t gpk_launch_count(void);
 void gpk_launch_count_reset(void);

@@ -54,6 +54,8 @@ _PLAIN = {
     "gpk_probe_dmma_tflops": ([], c_double),
     "gpk_launch_count": ([], _i64),
     "gpk_launch_count_reset": ([], None),
+    "gpk_gemm_profile_enable": ([_i32], None),
+    "gpk_gemm_profile_read": ([POINTER(c_double), POINTER(c_double), POINTER(_i64)], c_int32),
 }
 
 #: every symbol ``include/gpk.h`` declares (checked by tests/test_abi.py against the header text)

@@ -9,6 +9,8 @@
 //   k-group of 8 is permuted identically for A and B, which leaves the product unchanged).
 //   Roofline: fp64 tensor pipe (measured 37.1 TFLOP/s DMMA peak); algorithmic flops 2 M N K (M N K for lower).
 // fp32: classic register-tiled FFMA kernel (8 x 8 micro-tiles), double-buffered.
+#include <vector>
+
 #include "common.cuh"
 
 namespace gpk {
@@ -249,6 +251,26 @@ static int check_gemm_args(int64_t M, int64_t N, int64_t K, const T* A, int64_t 
   return 0;
 }
 
+// ---- in-situ timing of the dominant kernel (bench.py's roofline leg) ----------------------------------------------
+// When enabled, every fp64 GEMM launch is bracketed by two events on ITS OWN stream; gpk_gemm_profile_read() sums the
+// elapsed times and the algorithmic flops (2 * 128 * 128 * K per computed tile) after the caller has synchronised.
+struct GemmProfile {
+  bool enabled = false;
+  std::vector<cudaEvent_t> ev;  // pairs
+  std::vector<double> flops;
+};
+static GemmProfile g_prof;
+
+static void prof_begin(cudaStream_t s, double flops) {
+  cudaEvent_t a, b;
+  if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+  g_prof.ev.push_back(a);
+  g_prof.ev.push_back(b);
+  g_prof.flops.push_back(flops);
+  cudaEventRecord(a, s);
+}
+static void prof_end(cudaStream_t s) { cudaEventRecord(g_prof.ev.back(), s); }
+
 int gemm_nt_f64(int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, int64_t a_bs,
                 const double* B, int64_t ldb, int64_t b_bs, double beta, double* C, int64_t ldc, int64_t c_bs,
                 int32_t lower, int32_t batch, cudaStream_t stream) {
@@ -265,7 +287,13 @@ int gemm_nt_f64(int64_t M, int64_t N, int64_t K, double alpha, const double* A, 
     attr_set = true;
   }
   dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch);
+  if (g_prof.enabled) {
+    const double tn = (double)p.tiles_n, tmm = (double)p.tiles_m;
+    const double tiles = lower ? (tn * (tn + 1) / 2 + (tmm - tn) * tn) : tmm * tn;  // lower: tile_m >= tile_n
+    prof_begin(stream, tiles * 2.0 * GM_BM * GM_BN * (double)K * batch);
+  }
   gemm_nt_f64_kernel<<<grid, GM_THREADS, smem, stream>>>(p);
+  if (g_prof.enabled) prof_end(stream);
   GPK_COUNT_LAUNCH();
   GPK_CHECK_LAUNCH();
   return 0;
@@ -289,6 +317,27 @@ int gemm_nt_f32(int64_t M, int64_t N, int64_t K, float alpha, const float* A, in
 }  // namespace gpk
 
 extern "C" {
+void gpk_gemm_profile_enable(int32_t on) {
+  for (cudaEvent_t e : gpk::g_prof.ev) cudaEventDestroy(e);
+  gpk::g_prof.ev.clear();
+  gpk::g_prof.flops.clear();
+  gpk::g_prof.enabled = on != 0;
+}
+int gpk_gemm_profile_read(double* total_ms, double* total_flops, int64_t* launches) {
+  double ms = 0.0, fl = 0.0;
+  const size_t n = gpk::g_prof.flops.size();
+  for (size_t i = 0; i < n; ++i) {
+    float t = 0.f;
+    cudaError_t e = cudaEventElapsedTime(&t, gpk::g_prof.ev[2 * i], gpk::g_prof.ev[2 * i + 1]);
+    if (e != cudaSuccess) return -1000 - (int)e;
+    ms += t;
+    fl += gpk::g_prof.flops[i];
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = (int64_t)n;
+  return 0;
+}
 int gpk_gemm_nt_f64(int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, int64_t a_bstride,
                     const double* B, int64_t ldb, int64_t b_bstride, double beta, double* C, int64_t ldc,
                     int64_t c_bstride, int32_t lower, int32_t batch, void* stream) {

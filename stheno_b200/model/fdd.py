@@ -52,24 +52,27 @@ class FDD(Normal):
 
         dtype, device, origin, bshape = _input_meta(x)
         n = infer_size(p.kernel, x)
-        self.noise = _noise_as_matrix(noise, dtype, device, n, origin, bshape)
+        self.noise = noise_m = _noise_as_matrix(noise, dtype, device, n, origin, bshape)
 
+        # NB: the constructors close over (p, x, noise_m), never over `self`: no reference cycle, so the multi-GB
+        # factorisation workspace hanging off the variance is released by reference counting as soon as the FDD goes
+        # out of scope (and the caching allocator hands the same block to the next evaluation).
         def var():
-            return M.add(pairwise(p.kernel, x), self.noise)
+            return M.add(pairwise(p.kernel, x), noise_m)
 
         def mean():
             return p.mean.dev(x)
 
         def var_diag():
-            return _elwise_any(p.kernel, x, None, True).squeeze(-1) + M.diag(self.noise)
+            return _elwise_any(p.kernel, x, None, True).squeeze(-1) + M.diag(noise_m)
 
         def mv():
             m, v = mean_var(p.mean, p.kernel, x)
-            return m, M.add(v, self.noise)
+            return m, M.add(v, noise_m)
 
         def mvd():
             m, vd = mean_var_diag(p.mean, p.kernel, x)
-            return m, vd.squeeze(-1) + M.diag(self.noise)
+            return m, vd.squeeze(-1) + M.diag(noise_m)
 
         Normal.__init__(self, mean, var, var_diag=var_diag, mean_var=mv, mean_var_diag=mvd, origin=origin)
 

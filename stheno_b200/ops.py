@@ -383,6 +383,19 @@ def kernel_rows_padded(flat, xsg, xg, chol):
     return out
 
 
+def gemm_profile(enable):
+    """Switch the in-situ event timing of the fp64 GEMM kernel on / off (clears the record)."""
+    _lib.load().gpk_gemm_profile_enable(1 if enable else 0)
+
+
+def gemm_profile_read():
+    """``(total_ms, algorithmic_flops, launches)`` of the GEMM launches since ``gemm_profile(True)``; synchronises."""
+    torch.cuda.synchronize()
+    ms, fl, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+    check(_lib.load().gpk_gemm_profile_read(ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n)), "gpk_gemm_profile_read")
+    return ms.value, fl.value, n.value
+
+
 def probe_dmma_tflops():
     return float(_lib.load().gpk_probe_dmma_tflops())
 
