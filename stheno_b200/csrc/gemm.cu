@@ -9,6 +9,8 @@
 //   k-group of 8 is permuted identically for A and B, which leaves the product unchanged).
 //   Roofline: fp64 tensor pipe (measured 37.1 TFLOP/s DMMA peak); algorithmic flops 2 M N K (M N K for lower).
 // fp32: classic register-tiled FFMA kernel (8 x 8 micro-tiles), double-buffered.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -137,6 +139,169 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_nt_f64_kernel(const GemmPa
       }
       *cp = v;
     }
+}
+
+// ---- fp64 v2: persistent CTAs, 16 warps, operand prefetch running across tile boundaries ----------------------------
+// One CTA per SM loops over the valid output tiles (static striding over a grouped rasterisation that keeps the A/B
+// panels of concurrently processed tiles in L2).  The cp.async pipeline treats the CTA's whole sequence of
+// (tile, k-tile) steps as ONE stream, so the operands of the next tile are already in flight while the current tile's
+// last k-tiles and its epilogue run: the per-tile prologue bubble disappears (it is ~15 % of a K = 128 panel update).
+// 16 warps (4 x 4, warp tile 32 x 32) put four warps on every SM sub-partition: enough independent DMMA chains to keep
+// the fp64 tensor pipe busy across the per-k-tile barrier and the LDS latency (the 8-warp version idles it ~17 %).
+constexpr int G2_THREADS = 512;
+constexpr int G2_MAX_GROUPS = 448;
+
+struct Gemm2Params {
+  int64_t K;
+  double alpha, beta;
+  const double* A;
+  int64_t lda, a_bs;
+  const double* B;
+  int64_t ldb, b_bs;
+  double* C;
+  int64_t ldc, c_bs;
+  int32_t lower, tiles_m, tiles_n, n_groups;
+  int32_t tiles_per_batch, total_tiles;
+  int32_t group_prefix[G2_MAX_GROUPS + 1];  // lower mode: first valid-tile index of every 8-row group
+};
+
+__device__ __forceinline__ void g2_decode(const Gemm2Params& p, int idx, int& b, int& tm, int& tn) {
+  b = idx / p.tiles_per_batch;
+  int r = idx - b * p.tiles_per_batch;
+  if (!p.lower) {
+    tile_coords(r, p.tiles_m, p.tiles_n, tm, tn);
+    return;
+  }
+  int g = 0;
+  while (g + 1 < p.n_groups && p.group_prefix[g + 1] <= r) ++g;
+  r -= p.group_prefix[g];
+  const int first = g * 8;
+  const int gsize = min(p.tiles_m - first, 8);
+  const int c0 = min(first, p.tiles_n);  // columns left of the group's diagonal block: all gsize rows valid
+  if (r < c0 * gsize) {
+    tn = r / gsize;
+    tm = first + r - tn * gsize;
+    return;
+  }
+  r -= c0 * gsize;
+  for (int c = 0; c < gsize; ++c) {  // triangular part: column first + c holds rows first + c .. first + gsize - 1
+    const int cnt = gsize - c;
+    if (r < cnt) {
+      tn = first + c;
+      tm = tn + r;
+      return;
+    }
+    r -= cnt;
+  }
+  tn = 0;
+  tm = first;  // unreachable
+}
+
+__global__ void __launch_bounds__(G2_THREADS, 1) gemm_nt_f64_v2_kernel(const __grid_constant__ Gemm2Params p) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;  // 4 x 4 warps; warp tile 32 x 32
+  extern __shared__ __align__(16) double gm_smem[];
+  double* As = gm_smem;
+  double* Bs = gm_smem + GM_STAGES * GM_STAGE_ELEMS;
+
+  const int KT = (int)(p.K / GM_BK);
+  const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_iters = my_tiles * KT;
+
+  // loader state: the (tile, k-tile) the next load belongs to
+  const int ld_row = tid >> 3, ld_g = tid & 7;  // rows ld_row, ld_row + 64; granule ld_g
+  const int ld_slot = ((ld_g >> 2) * 32 + (ld_row & 7) * 4 + (ld_g & 3)) * 2;
+  int ld_it = 0, ld_kt = 0, ld_tile = blockIdx.x;
+  const double *ld_a = nullptr, *ld_b = nullptr;
+  auto load_next = [&]() {
+    if (ld_it < total_iters) {
+      if (ld_kt == 0) {
+        int b, tm, tn;
+        g2_decode(p, ld_tile, b, tm, tn);
+        ld_a = p.A + (int64_t)b * p.a_bs + ((int64_t)tm * GM_BM + ld_row) * p.lda + ld_g * 2;
+        ld_b = p.B + (int64_t)b * p.b_bs + ((int64_t)tn * GM_BN + ld_row) * p.ldb + ld_g * 2;
+      }
+      const int slot = ld_it % GM_STAGES;
+      double* as = As + slot * GM_STAGE_ELEMS + (ld_row >> 3) * 128 + ld_slot;
+      double* bs = Bs + slot * GM_STAGE_ELEMS + (ld_row >> 3) * 128 + ld_slot;
+      const int64_t koff = (int64_t)ld_kt * GM_BK;
+      cp_async16(as, ld_a + koff);
+      cp_async16(as + 8 * 128, ld_a + 64 * p.lda + koff);  // row + 64 -> row block + 8
+      cp_async16(bs, ld_b + koff);
+      cp_async16(bs + 8 * 128, ld_b + 64 * p.ldb + koff);
+      ++ld_it;
+      if (++ld_kt == KT) {
+        ld_kt = 0;
+        ld_tile += gridDim.x;
+      }
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int s = 0; s < GM_STAGES - 1; ++s) load_next();
+
+  double acc[4][4][2];
+  int it = 0;
+  for (int t = 0; t < my_tiles; ++t) {
+    int b, tm, tn;
+    g2_decode(p, (int)blockIdx.x + t * (int)gridDim.x, b, tm, tn);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kt = 0; kt < KT; ++kt, ++it) {
+      cp_async_wait<GM_STAGES - 2>();
+      __syncthreads();
+      load_next();
+      const double* as = As + (it % GM_STAGES) * GM_STAGE_ELEMS + (wm * 4) * 128 + lane * 2;
+      const double* bs = Bs + (it % GM_STAGES) * GM_STAGE_ELEMS + (wn * 4) * 128 + lane * 2;
+#pragma unroll
+      for (int k8 = 0; k8 < 2; ++k8) {
+        double2 a[4], bb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const double2*>(as + i * 128 + k8 * 64);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bb[j] = *reinterpret_cast<const double2*>(bs + j * 128 + k8 * 64);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            dmma884(acc[i][j][0], acc[i][j][1], a[i].x, bb[j].x);
+            dmma884(acc[i][j][0], acc[i][j][1], a[i].y, bb[j].y);
+          }
+      }
+    }
+
+    double* Cg = p.C + (int64_t)b * p.c_bs + ((int64_t)tm * GM_BM + wm * 32 + (lane >> 2)) * p.ldc +
+                 (int64_t)tn * GM_BN + wn * 32 + 2 * (lane & 3);
+    const double alpha = p.alpha, beta = p.beta;
+    if (beta != 0.0) {
+      double2 old[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) old[i][j] = *reinterpret_cast<const double2*>(Cg + (int64_t)i * 8 * p.ldc + j * 8);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          double2 v;
+          v.x = fma(alpha, acc[i][j][0], beta * old[i][j].x);
+          v.y = fma(alpha, acc[i][j][1], beta * old[i][j].y);
+          *reinterpret_cast<double2*>(Cg + (int64_t)i * 8 * p.ldc + j * 8) = v;
+        }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<double2*>(Cg + (int64_t)i * 8 * p.ldc + j * 8) =
+              make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
+    }
+  }
+  cp_async_wait<0>();
 }
 
 // ---- fp32: register-tiled FFMA ------------------------------------------------------------------------
@@ -277,10 +442,50 @@ int gemm_nt_f64(int64_t M, int64_t N, int64_t K, double alpha, const double* A, 
   int rc = check_gemm_args<double>(M, N, K, A, lda, B, ldb, C, ldc, batch);
   if (rc) return rc;
   if (M == 0 || N == 0) return 0;
-  GemmParams<double> p{M, N, K, alpha, beta, A, lda, a_bs, B, ldb, b_bs, C, ldc, c_bs, lower,
-                       (int32_t)(M / GM_BM), (int32_t)(N / GM_BN)};
-  static bool attr_set = false;
+  const int32_t tiles_m = (int32_t)(M / GM_BM), tiles_n = (int32_t)(N / GM_BN);
   const int smem = 2 * GM_STAGES * GM_STAGE_ELEMS * (int)sizeof(double);
+  const int n_groups = (tiles_m + 7) / 8;
+  static const bool force_v1 = getenv("GPK_GEMM_V1") != nullptr;
+  if (!force_v1 && K > 0 && (!lower || n_groups <= G2_MAX_GROUPS) && (int64_t)tiles_m * tiles_n * batch < (1ll << 30)) {
+    static Gemm2Params q;  // large (group table): filled in place, passed by value at launch
+    q.K = K; q.alpha = alpha; q.beta = beta; q.A = A; q.lda = lda; q.a_bs = a_bs; q.B = B; q.ldb = ldb; q.b_bs = b_bs;
+    q.C = C; q.ldc = ldc; q.c_bs = c_bs; q.lower = lower; q.tiles_m = tiles_m; q.tiles_n = tiles_n;
+    q.n_groups = n_groups;
+    int per_batch;
+    if (lower) {
+      int acc = 0;
+      for (int g = 0; g < n_groups; ++g) {
+        q.group_prefix[g] = acc;
+        const int first = g * 8, gsize = (tiles_m - first < 8) ? tiles_m - first : 8;
+        for (int r = 0; r < gsize; ++r) acc += (first + r + 1 < tiles_n) ? first + r + 1 : tiles_n;
+      }
+      q.group_prefix[n_groups] = acc;
+      per_batch = acc;
+    } else {
+      per_batch = tiles_m * tiles_n;
+    }
+    q.tiles_per_batch = per_batch;
+    q.total_tiles = per_batch * batch;
+    static int num_sms = 0;
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaError_t e = cudaFuncSetAttribute(gemm_nt_f64_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return -1000 - (int)e;
+      attr2_set = true;
+    }
+    const int grid = q.total_tiles < num_sms ? q.total_tiles : num_sms;
+    if (g_prof.enabled) prof_begin(stream, (double)q.total_tiles * 2.0 * GM_BM * GM_BN * (double)K);
+    gemm_nt_f64_v2_kernel<<<grid, G2_THREADS, smem, stream>>>(q);
+    if (g_prof.enabled) prof_end(stream);
+    GPK_COUNT_LAUNCH();
+    GPK_CHECK_LAUNCH();
+    return 0;
+  }
+  GemmParams<double> p{M, N, K, alpha, beta, A, lda, a_bs, B, ldb, b_bs, C, ldc, c_bs, lower, tiles_m, tiles_n};
+  static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_nt_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return -1000 - (int)e;
