@@ -99,6 +99,18 @@ int gpk_kernel_diag_f32(const gpk_kernel_desc* desc_host, const float* xg, int64
                         const float* yg, int64_t yg_gstride, int64_t y_bstride, int64_t n, int32_t d, int32_t same,
                         float* out, int64_t o_bstride, int32_t batch, void* stream);
 
+/* K1-backward: contraction of an upstream gradient G = d(loss)/dK (symmetric n x n, ld = ldg) with dK/d(theta) for
+ * K = k(x, x) (same points): term_sum[b][t] += sum_ij G_ij prod_f phi_f  (d loss / d coef_t; caller zeroes it; stride
+ * GPK_MAX_TERMS), grad_xg[g][b][i][:] = d loss / d x^(g)_i (layout and strides of xg), diag[b][i] = G_ii (noise
+ * gradient).  No n x n tensor per hyper-parameter is ever formed.  Replaces torch autograd through
+ * exp / pw_dists2 in the reference's optimisation loop (readme_example13_optimisation_torch.py:46-53). */
+int gpk_kernel_matrix_bwd_f64(const gpk_kernel_desc* desc_host, const double* xg, int64_t xg_gstride,
+                              int64_t x_bstride, int64_t n, int32_t d, const double* G, int64_t ldg, int64_t g_bstride,
+                              double* term_sum, double* grad_xg, double* diag, int32_t batch, void* stream);
+int gpk_kernel_matrix_bwd_f32(const gpk_kernel_desc* desc_host, const float* xg, int64_t xg_gstride, int64_t x_bstride,
+                              int64_t n, int32_t d, const float* G, int64_t ldg, int64_t g_bstride, float* term_sum,
+                              float* grad_xg, float* diag, int32_t batch, void* stream);
+
 /* GEMM  C = beta*C + alpha * A * B^T   (A: M x K, B: N x K, both K-contiguous; C: M x N).
  * M, N multiples of 128; K a multiple of 16; pointers 16-byte aligned; ld multiples of 2.
  * lower != 0: only tiles with (row tile >= col tile) are touched (SYRK-style trailing update, M >= N).

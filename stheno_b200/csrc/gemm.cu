@@ -108,13 +108,15 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_nt_f64_kernel(const GemmPa
       for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const double2*>(as + i * 128 + k8 * 64);
 #pragma unroll
       for (int j = 0; j < 4; ++j) bb[j] = *reinterpret_cast<const double2*>(bs + j * 128 + k8 * 64);
+      // even-k pass over all 32 accumulators, then the odd-k pass: dependent DMMAs are 32 instructions apart
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          dmma884(acc[i][j][0], acc[i][j][1], a[i].x, bb[j].x);
-          dmma884(acc[i][j][0], acc[i][j][1], a[i].y, bb[j].y);
-        }
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, bb[j].x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, bb[j].y);
     }
   }
   cp_async_wait<0>();
@@ -267,10 +269,11 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm_nt_f64_v2_kernel(const __g
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            dmma884(acc[i][j][0], acc[i][j][1], a[i].x, bb[j].x);
-            dmma884(acc[i][j][0], acc[i][j][1], a[i].y, bb[j].y);
-          }
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, bb[j].x);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, bb[j].y);
       }
     }
 
@@ -476,7 +479,12 @@ int gemm_nt_f64(int64_t M, int64_t N, int64_t K, double alpha, const double* A, 
       if (e != cudaSuccess) return -1000 - (int)e;
       attr2_set = true;
     }
-    const int grid = q.total_tiles < num_sms ? q.total_tiles : num_sms;
+    // Small-K updates (panel steps) run persistent: the cross-tile prefetch hides their per-tile prologue.  Large-K
+    // trailing updates launch one CTA per tile instead, so that CTAs retire continuously and the high-priority
+    // look-ahead kernels of the side stream can get SMs while the update is in flight.
+    static const bool force_persistent = getenv("GPK_GEMM_PERSISTENT") != nullptr;
+    const bool persistent = force_persistent || K < 512;
+    const int grid = (persistent && q.total_tiles > num_sms) ? num_sms : q.total_tiles;
     if (g_prof.enabled) prof_begin(stream, (double)q.total_tiles * 2.0 * GM_BM * GM_BN * (double)K);
     gemm_nt_f64_v2_kernel<<<grid, G2_THREADS, smem, stream>>>(q);
     if (g_prof.enabled) prof_end(stream);

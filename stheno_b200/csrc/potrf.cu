@@ -293,14 +293,18 @@ trsm_leaf_tc_f64_kernel(const double* __restrict__ L, int64_t ldl, int64_t l_bs,
     acc[2 * jb + 1][0] = x[1][0];
     acc[2 * jb + 1][1] = x[1][1];
     const double nx[2][2] = {{-x[0][0], -x[0][1]}, {-x[1][0], -x[1][1]}};
+    // four passes (k-group x parity) over all later column blocks: consecutive DMMAs hit different accumulators
 #pragma unroll
-    for (int cb = 2 * jb + 2; cb < 16; ++cb)
+    for (int kg = 0; kg < 2; ++kg) {
+      double2 b[16];
 #pragma unroll
-      for (int kg = 0; kg < 2; ++kg) {
-        const double2 b = *reinterpret_cast<const double2*>(Lf + (cb * 16 + 2 * jb + kg) * 64);
-        dmma884(acc[cb][0], acc[cb][1], nx[kg][0], b.x);
-        dmma884(acc[cb][0], acc[cb][1], nx[kg][1], b.y);
-      }
+      for (int cb = 2 * jb + 2; cb < 16; ++cb)
+        b[cb] = *reinterpret_cast<const double2*>(Lf + (cb * 16 + 2 * jb + kg) * 64);
+#pragma unroll
+      for (int cb = 2 * jb + 2; cb < 16; ++cb) dmma884(acc[cb][0], acc[cb][1], nx[kg][0], b[cb].x);
+#pragma unroll
+      for (int cb = 2 * jb + 2; cb < 16; ++cb) dmma884(acc[cb][0], acc[cb][1], nx[kg][1], b[cb].y);
+    }
   }
 #pragma unroll
   for (int cb = 0; cb < 16; ++cb) *reinterpret_cast<double2*>(Bw + cb * 8) = make_double2(acc[cb][0], acc[cb][1]);

@@ -197,7 +197,7 @@ class Kernel:
         if terms is None:
             return None, None
         scales, keys = [], {}
-        out = []
+        out, raw = [], []
         for coef, fs in terms:
             nf = []
             for kind, s in fs:
@@ -207,9 +207,13 @@ class Kernel:
                     scales.append(s)
                 nf.append((kind, keys[k]))
             out.append((float(coef), nf))
+            raw.append(coef)
         if not scales:
             scales = [None]
-        return ops.FlatKernel(out, len(scales)), scales
+        flat = ops.FlatKernel(out, len(scales))
+        # hyper-parameters given as torch tensors that require grad: remember them for the differentiable path
+        flat.coef_raw = raw if any(isinstance(c, torch.Tensor) and c.requires_grad for c in raw) else None
+        return flat, scales
 
     def _pairwise_dev(self, x, y, same):
         """Device tensor ``[..., n, m]`` for numeric inputs ``x, y`` (:class:`Input`)."""
@@ -347,7 +351,7 @@ class ScaledKernel(Kernel):
         t = self.k.flat_terms()
         if t is None:
             return None
-        s = float(self.scale)
+        s = self.scale if isinstance(self.scale, torch.Tensor) else float(self.scale)
         return [(c * s, fs) for c, fs in t]
 
     def _pairwise_dev(self, x, y, same):

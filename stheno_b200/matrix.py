@@ -149,18 +149,20 @@ class KernelDense(Dense):
     """``k(x, x) + noise`` kept symbolic: ``flat`` kernel, stretched inputs ``xg [G, B, n, d]``, diagonal noise.
 
     ``dev`` materialises the full matrix with K1; ``chol()`` never does -- it builds the padded lower triangle
-    (+ noise + jitter) in place and factorises it."""
+    (+ noise + jitter) in place and factorises it.  ``noise_t`` keeps a scalar noise given as a torch tensor that
+    requires grad (``needs_grad`` then routes ``logpdf`` through ``autograd.kernel_logpdf``)."""
 
-    def __init__(self, flat, xg, batch_shape, noise_scalar=0.0, noise_vec=None, origin=None):
+    def __init__(self, flat, xg, batch_shape, noise_scalar=0.0, noise_vec=None, origin=None, noise_t=None):
         super().__init__(None, origin)
         self.flat, self.xg, self.batch_shape = flat, xg, tuple(batch_shape)
-        self.noise_scalar, self.noise_vec = float(noise_scalar), noise_vec
+        self.noise_scalar, self.noise_vec, self.noise_t = float(noise_scalar), noise_vec, noise_t
         self.n = xg.shape[2]
 
     @property
     def dev(self):
         if self._mat is None:
-            K = ops.kernel_matrix(self.flat, self.xg, noise_scalar=self.noise_scalar, noise_vec=self.noise_vec)
+            K = ops.kernel_matrix(self.flat, self.xg.detach(), noise_scalar=self.noise_scalar,
+                                  noise_vec=None if self.noise_vec is None else self.noise_vec.detach())
             self._mat = K.reshape(self.batch_shape + (self.n, self.n))
         return self._mat
 
@@ -176,26 +178,58 @@ class KernelDense(Dense):
     def device(self):
         return self.xg.device
 
-    def with_noise(self, scalar=0.0, vec=None):
+    def needs_grad(self):
+        return torch.is_grad_enabled() and (
+            getattr(self.flat, "coef_raw", None) is not None
+            or self.xg.requires_grad
+            or (self.noise_t is not None and self.noise_t.requires_grad)
+            or (self.noise_vec is not None and self.noise_vec.requires_grad)
+        )
+
+    def with_noise(self, scalar=0.0, vec=None, scalar_t=None):
         """``self + Diagonal`` stays symbolic."""
         nv = self.noise_vec
         if vec is not None:
             v3 = vec.reshape(-1, self.n) if vec.dim() > 1 else vec.reshape(1, self.n).expand(self.xg.shape[1], self.n)
             nv = v3 if nv is None else nv + v3
-        return KernelDense(self.flat, self.xg, self.batch_shape, self.noise_scalar + float(scalar), nv, self.origin)
+        nt = self.noise_t
+        if scalar_t is not None:
+            nt = (self.noise_scalar if nt is None else nt) + scalar_t
+        elif nt is not None:
+            nt = nt + float(scalar)
+        return KernelDense(self.flat, self.xg, self.batch_shape, self.noise_scalar + float(scalar), nv, self.origin, nt)
 
     def _factorize(self, rhs_t):
-        return ops.chol_from_kernel(self.flat, self.xg, noise_scalar=self.noise_scalar, noise_vec=self.noise_vec,
+        return ops.chol_from_kernel(self.flat, self.xg.detach(), noise_scalar=self.noise_scalar,
+                                    noise_vec=None if self.noise_vec is None else self.noise_vec.detach(),
                                     jitter=_B.epsilon, rhs_t=rhs_t)
+
+    def logpdf_grad(self, rhs_t):
+        """Differentiable ``logpdf`` ``[B, k]`` w.r.t. kernel scales, length scales / inputs (through ``xg``), noise and
+        the right-hand sides."""
+        from .autograd import kernel_logpdf
+
+        raw = getattr(self.flat, "coef_raw", None) or [c for c, _ in self.flat.terms]
+        coefs = torch.stack([
+            (c if isinstance(c, torch.Tensor) else torch.tensor(float(c))).to(device=self.xg.device, dtype=self.xg.dtype).reshape(())
+            for c in raw
+        ])
+        if self.noise_t is not None:
+            ns = self.noise_t.to(device=self.xg.device, dtype=self.xg.dtype).reshape(())
+        else:
+            ns = torch.tensor(self.noise_scalar, device=self.xg.device, dtype=self.xg.dtype)
+        structure = [fs for _, fs in self.flat.terms]
+        return kernel_logpdf(coefs, self.xg, ns, self.noise_vec, rhs_t, structure, _B.epsilon)
 
 
 class Diagonal(AbstractMatrix):
     """Diagonal matrix with diagonal ``diag [..., n]``.  ``scalar`` is set when the diagonal is constant."""
 
-    def __init__(self, diag_, origin=None, scalar=None):
+    def __init__(self, diag_, origin=None, scalar=None, scalar_t=None):
         self.diag = diag_
         self.origin = origin
         self.scalar = scalar
+        self.scalar_t = scalar_t  # the scalar as a torch tensor with a graph (differentiable noise)
 
     @property
     def dev(self):
@@ -324,7 +358,7 @@ def add(a, b):
     if isinstance(b, Diagonal):
         if isinstance(a, KernelDense) and a._mat is None and a._chol is None:
             if b.scalar is not None:
-                return a.with_noise(scalar=b.scalar)
+                return a.with_noise(scalar=b.scalar, scalar_t=getattr(b, "scalar_t", None))
             return a.with_noise(vec=b.diag)
         m = a.dev.clone()
         torch.diagonal(m, dim1=-2, dim2=-1).add_(b.diag)

@@ -27,6 +27,10 @@ def _noise_as_matrix(noise, dtype, device, n, origin, batch_shape=()):
     if isinstance(noise, M.AbstractMatrix):
         return noise
     if isinstance(noise, (int, float, np.number)) or (isinstance(noise, (np.ndarray, torch.Tensor)) and noise.ndim == 0):
+        if isinstance(noise, torch.Tensor) and noise.requires_grad:
+            shape = tuple(batch_shape) + (n,)
+            return M.Diagonal(noise.to(device=device, dtype=dtype).expand(shape), origin, scalar=float(noise),
+                              scalar_t=noise)
         if batch_shape:
             v = float(noise)
             return M.Diagonal(torch.full(tuple(batch_shape) + (n,), v, dtype=dtype, device=device), origin, scalar=v)

@@ -208,7 +208,9 @@ class Normal(RandomVector):
         else:
             d3, bs = batch_flatten(diff, 2)
             rhs_t = d3.transpose(1, 2).contiguous()  # [B, k, n]: right-hand sides as rows
-            if var._chol is None:
+            if isinstance(var, M.KernelDense) and (var.needs_grad() or (torch.is_grad_enabled() and rhs_t.requires_grad)):
+                lp = var.logpdf_grad(rhs_t)  # analytic backward (autograd.py)
+            elif var._chol is None:
                 key = ("logpdf", id(xd))
                 var.attach_rhs(key, rhs_t)
                 ch = var.chol()
