@@ -199,21 +199,30 @@ __device__ __forceinline__ void g2_decode(const Gemm2Params& p, int idx, int& b,
   tm = first;  // unreachable
 }
 
+// BK x STAGES: 16 x 4 (128 KB) or 32 x 3 (192 KB).  The deeper k-tile halves the number of barrier / wait_group /
+// address-recompute episodes per flop -- ncu shows the DMMA pipe idling ~18 % of the time around them with BK = 16.
+template <int BK, int STAGES>
 __global__ void __launch_bounds__(G2_THREADS, 1) gemm_nt_f64_v2_kernel(const __grid_constant__ Gemm2Params p) {
+  constexpr int K8 = BK / 8;                 // k8-groups per k-tile
+  constexpr int STAGE_ELEMS = GM_BM * BK;    // per operand per stage
+  constexpr int RB = K8 * 64;                // doubles per 8-row block
+  constexpr int GPR = BK / 2;                // 16-byte granules per row
+  constexpr int ROWS_PER_PASS = G2_THREADS / GPR;
+  constexpr int PASSES = GM_BM / ROWS_PER_PASS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;  // 4 x 4 warps; warp tile 32 x 32
   extern __shared__ __align__(16) double gm_smem[];
   double* As = gm_smem;
-  double* Bs = gm_smem + GM_STAGES * GM_STAGE_ELEMS;
+  double* Bs = gm_smem + STAGES * STAGE_ELEMS;
 
-  const int KT = (int)(p.K / GM_BK);
+  const int KT = (int)(p.K / BK);
   const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total_iters = my_tiles * KT;
 
-  // loader state: the (tile, k-tile) the next load belongs to
-  const int ld_row = tid >> 3, ld_g = tid & 7;  // rows ld_row, ld_row + 64; granule ld_g
-  const int ld_slot = ((ld_g >> 2) * 32 + (ld_row & 7) * 4 + (ld_g & 3)) * 2;
-  int ld_it = 0, ld_kt = 0, ld_tile = blockIdx.x;
+  // loader: thread copies granule ld_g of rows ld_row + ROWS_PER_PASS * i
+  const int ld_row = tid / GPR, ld_g = tid % GPR;
+  const int ld_off = (ld_row >> 3) * RB + ((ld_g >> 2) * 32 + (ld_row & 7) * 4 + (ld_g & 3)) * 2;
+  int ld_it = 0, ld_kt = 0, ld_tile = blockIdx.x, ld_slot = 0;
   const double *ld_a = nullptr, *ld_b = nullptr;
   auto load_next = [&]() {
     if (ld_it < total_iters) {
@@ -223,15 +232,16 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm_nt_f64_v2_kernel(const __g
         ld_a = p.A + (int64_t)b * p.a_bs + ((int64_t)tm * GM_BM + ld_row) * p.lda + ld_g * 2;
         ld_b = p.B + (int64_t)b * p.b_bs + ((int64_t)tn * GM_BN + ld_row) * p.ldb + ld_g * 2;
       }
-      const int slot = ld_it % GM_STAGES;
-      double* as = As + slot * GM_STAGE_ELEMS + (ld_row >> 3) * 128 + ld_slot;
-      double* bs = Bs + slot * GM_STAGE_ELEMS + (ld_row >> 3) * 128 + ld_slot;
-      const int64_t koff = (int64_t)ld_kt * GM_BK;
-      cp_async16(as, ld_a + koff);
-      cp_async16(as + 8 * 128, ld_a + 64 * p.lda + koff);  // row + 64 -> row block + 8
-      cp_async16(bs, ld_b + koff);
-      cp_async16(bs + 8 * 128, ld_b + 64 * p.ldb + koff);
+      double* as = As + ld_slot * STAGE_ELEMS + ld_off;
+      double* bs = Bs + ld_slot * STAGE_ELEMS + ld_off;
+      const int64_t koff = (int64_t)ld_kt * BK;
+#pragma unroll
+      for (int i = 0; i < PASSES; ++i) {
+        cp_async16(as + i * (ROWS_PER_PASS / 8) * RB, ld_a + (int64_t)i * ROWS_PER_PASS * p.lda + koff);
+        cp_async16(bs + i * (ROWS_PER_PASS / 8) * RB, ld_b + (int64_t)i * ROWS_PER_PASS * p.ldb + koff);
+      }
       ++ld_it;
+      if (++ld_slot == STAGES) ld_slot = 0;
       if (++ld_kt == KT) {
         ld_kt = 0;
         ld_tile += gridDim.x;
@@ -241,10 +251,11 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm_nt_f64_v2_kernel(const __g
   };
 
 #pragma unroll
-  for (int s = 0; s < GM_STAGES - 1; ++s) load_next();
+  for (int s = 0; s < STAGES - 1; ++s) load_next();
 
   double acc[4][4][2];
-  int it = 0;
+  int slot = 0;
+  const int frag_a = (wm * 4) * RB + lane * 2, frag_b = (wn * 4) * RB + lane * 2;
   for (int t = 0; t < my_tiles; ++t) {
     int b, tm, tn;
     g2_decode(p, (int)blockIdx.x + t * (int)gridDim.x, b, tm, tn);
@@ -253,28 +264,31 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm_nt_f64_v2_kernel(const __g
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    for (int kt = 0; kt < KT; ++kt, ++it) {
-      cp_async_wait<GM_STAGES - 2>();
+    for (int kt = 0; kt < KT; ++kt) {
+      cp_async_wait<STAGES - 2>();
       __syncthreads();
-      load_next();
-      const double* as = As + (it % GM_STAGES) * GM_STAGE_ELEMS + (wm * 4) * 128 + lane * 2;
-      const double* bs = Bs + (it % GM_STAGES) * GM_STAGE_ELEMS + (wn * 4) * 128 + lane * 2;
+      const double* as = As + slot * STAGE_ELEMS + frag_a;
+      const double* bs = Bs + slot * STAGE_ELEMS + frag_b;
 #pragma unroll
-      for (int k8 = 0; k8 < 2; ++k8) {
+      for (int k8 = 0; k8 < K8; ++k8) {
         double2 a[4], bb[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const double2*>(as + i * 128 + k8 * 64);
+        for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const double2*>(as + i * RB + k8 * 64);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bb[j] = *reinterpret_cast<const double2*>(bs + j * 128 + k8 * 64);
+        for (int j = 0; j < 4; ++j) bb[j] = *reinterpret_cast<const double2*>(bs + j * RB + k8 * 64);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, bb[j].x);
+        // refill the slot freed by the previous k-tile once the tensor pipe has work queued (not right after the
+        // barrier, where it would delay the first DMMAs of all 16 warps)
+        if (k8 == 0) load_next();
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, bb[j].y);
       }
+      if (++slot == STAGES) slot = 0;
     }
 
     double* Cg = p.C + (int64_t)b * p.c_bs + ((int64_t)tm * GM_BM + wm * 32 + (lane >> 2)) * p.ldc +
@@ -471,11 +485,16 @@ int gemm_nt_f64(int64_t M, int64_t N, int64_t K, double alpha, const double* A, 
     q.total_tiles = per_batch * batch;
     static int num_sms = 0;
     static bool attr2_set = false;
+    constexpr int smem16 = 2 * 4 * GM_BM * 16 * (int)sizeof(double);  // BK = 16, 4 stages: 128 KB
+    constexpr int smem32 = 2 * 3 * GM_BM * 32 * (int)sizeof(double);  // BK = 32, 3 stages: 192 KB
     if (!attr2_set) {
       int dev = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaError_t e = cudaFuncSetAttribute(gemm_nt_f64_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaError_t e = cudaFuncSetAttribute(gemm_nt_f64_v2_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           smem16);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_nt_f64_v2_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
       if (e != cudaSuccess) return -1000 - (int)e;
       attr2_set = true;
     }
@@ -483,10 +502,14 @@ int gemm_nt_f64(int64_t M, int64_t N, int64_t K, double alpha, const double* A, 
     // trailing updates launch one CTA per tile instead, so that CTAs retire continuously and the high-priority
     // look-ahead kernels of the side stream can get SMs while the update is in flight.
     static const bool force_persistent = getenv("GPK_GEMM_PERSISTENT") != nullptr;
+    static const bool force_bk16 = getenv("GPK_GEMM_BK16") != nullptr;
     const bool persistent = force_persistent || K < 512;
     const int grid = (persistent && q.total_tiles > num_sms) ? num_sms : q.total_tiles;
     if (g_prof.enabled) prof_begin(stream, (double)q.total_tiles * 2.0 * GM_BM * GM_BN * (double)K);
-    gemm_nt_f64_v2_kernel<<<grid, G2_THREADS, smem, stream>>>(q);
+    if (K % 32 == 0 && !force_bk16)
+      gemm_nt_f64_v2_kernel<32, 3><<<grid, G2_THREADS, smem32, stream>>>(q);
+    else
+      gemm_nt_f64_v2_kernel<16, 4><<<grid, G2_THREADS, smem16, stream>>>(q);
     if (g_prof.enabled) prof_end(stream);
     GPK_COUNT_LAUNCH();
     GPK_CHECK_LAUNCH();

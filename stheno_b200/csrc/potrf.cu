@@ -222,9 +222,11 @@ __device__ __forceinline__ int frag_index(int n, int k) {
   return (((n >> 3) * 16 + (k >> 3)) * 32 + (n & 7) * 4 + ((k & 7) >> 1)) * 2 + (k & 1);
 }
 
+// T = storage type (double or float).  The arithmetic is always fp64 on the DMMA pipe: for fp32 problems the leaf TRSM is
+// < 2 % of the flops, and doing it in fp64 costs nothing while removing one source of fp32 round-off.
+template <typename T>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-trsm_leaf_tc_f64_kernel(const double* __restrict__ L, int64_t ldl, int64_t l_bs, double* __restrict__ B, int64_t ldb,
-                        int64_t b_bs) {
+trsm_leaf_tc_kernel(const T* __restrict__ L, int64_t ldl, int64_t l_bs, T* __restrict__ B, int64_t ldb, int64_t b_bs) {
   extern __shared__ __align__(16) unsigned char tc_smem[];
   double* Ls = reinterpret_cast<double*>(tc_smem);  // 128 x 128 fragment-major
   double* Ld = Ls + NB * NB;                         // [8][16][17] diagonal blocks (natural layout)
@@ -238,8 +240,9 @@ trsm_leaf_tc_f64_kernel(const double* __restrict__ L, int64_t ldl, int64_t l_bs,
     const int k = 2 * g;
     double2 v = make_double2(0.0, 0.0);
     if (k <= c) {
-      v = *reinterpret_cast<const double2*>(L + (int64_t)c * ldl + k);
-      if (k + 1 > c) v.y = 0.0;
+      const T* src = L + (int64_t)c * ldl + k;
+      v.x = (double)src[0];
+      v.y = (k + 1 > c) ? 0.0 : (double)src[1];
     }
     *reinterpret_cast<double2*>(Ls + frag_index(c, k)) = v;
     if ((c >> 4) == (k >> 4)) {  // diagonal 16 x 16 block: natural copy for the inversion
@@ -268,12 +271,11 @@ trsm_leaf_tc_f64_kernel(const double* __restrict__ L, int64_t ldl, int64_t l_bs,
 
   // (3) this warp's 8 rows as sixteen accumulator fragments
   double acc[16][2];
-  double* Bw = B + (int64_t)(warp * 8 + (lane >> 2)) * ldb + 2 * (lane & 3);
+  T* Bw = B + (int64_t)(warp * 8 + (lane >> 2)) * ldb + 2 * (lane & 3);
 #pragma unroll
   for (int cb = 0; cb < 16; ++cb) {
-    const double2 v = *reinterpret_cast<const double2*>(Bw + cb * 8);
-    acc[cb][0] = v.x;
-    acc[cb][1] = v.y;
+    acc[cb][0] = (double)Bw[cb * 8];
+    acc[cb][1] = (double)Bw[cb * 8 + 1];
   }
   const double* Lf = Ls + lane * 2;  // fragment (row block rb, k8 group kg) at Lf + (rb * 16 + kg) * 64
 #pragma unroll
@@ -307,21 +309,25 @@ trsm_leaf_tc_f64_kernel(const double* __restrict__ L, int64_t ldl, int64_t l_bs,
     }
   }
 #pragma unroll
-  for (int cb = 0; cb < 16; ++cb) *reinterpret_cast<double2*>(Bw + cb * 8) = make_double2(acc[cb][0], acc[cb][1]);
+  for (int cb = 0; cb < 16; ++cb) {
+    Bw[cb * 8] = (T)acc[cb][0];
+    Bw[cb * 8 + 1] = (T)acc[cb][1];
+  }
 }
 
-static int launch_trsm_leaf_tc_f64(const double* L, int64_t ldl, int64_t l_bs, double* B, int64_t ldb, int64_t b_bs,
-                                   int64_t rows, int32_t batch, cudaStream_t stream) {
+template <typename T>
+static int launch_trsm_leaf_tc(const T* L, int64_t ldl, int64_t l_bs, T* B, int64_t ldb, int64_t b_bs, int64_t rows,
+                               int32_t batch, cudaStream_t stream) {
   if (rows == 0) return 0;
   const int smem = (NB * NB + 8 * 16 * 17) * (int)sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(trsm_leaf_tc_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(trsm_leaf_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return -1000 - (int)e;
     attr_set = true;
   }
   dim3 grid((unsigned)(rows / TC_ROWS), (unsigned)batch);
-  trsm_leaf_tc_f64_kernel<<<grid, TC_THREADS, smem, stream>>>(L, ldl, l_bs, B, ldb, b_bs);
+  trsm_leaf_tc_kernel<T><<<grid, TC_THREADS, smem, stream>>>(L, ldl, l_bs, B, ldb, b_bs);
   GPK_COUNT_LAUNCH();
   GPK_CHECK_LAUNCH();
   return 0;
@@ -358,13 +364,8 @@ static int launch_trsm_leaf(const T* L, int64_t ldl, int64_t l_bs, T* B, int64_t
 template <typename T>
 static int trsm_leaf_fwd(const T* L, int64_t ldl, int64_t l_bs, T* B, int64_t ldb, int64_t b_bs, int64_t rows,
                          int32_t batch, cudaStream_t stream) {
+  if (rows % TC_ROWS == 0) return launch_trsm_leaf_tc<T>(L, ldl, l_bs, B, ldb, b_bs, rows, batch, stream);
   return launch_trsm_leaf<T, false>(L, ldl, l_bs, B, ldb, b_bs, rows, batch, stream);
-}
-template <>
-int trsm_leaf_fwd<double>(const double* L, int64_t ldl, int64_t l_bs, double* B, int64_t ldb, int64_t b_bs,
-                          int64_t rows, int32_t batch, cudaStream_t stream) {
-  if (rows % TC_ROWS == 0) return launch_trsm_leaf_tc_f64(L, ldl, l_bs, B, ldb, b_bs, rows, batch, stream);
-  return launch_trsm_leaf<double, false>(L, ldl, l_bs, B, ldb, b_bs, rows, batch, stream);
 }
 
 constexpr int64_t NB_OUTER = 1024;
