@@ -321,6 +321,118 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm_nt_f64_v2_kernel(const __g
   cp_async_wait<0>();
 }
 
+// ---- fp64 v3: 128 x 64 tiles, 8 warps, TWO CTAs per SM ------------------------------------------------------------------
+// For the large-K trailing updates.  One tile per CTA (CTAs retire continuously, so the high-priority look-ahead kernels
+// get SMs), and two co-resident CTAs per SM (96 KB smem, 128 registers x 256 threads each): while one CTA sits in its
+// barrier / prologue / C read-modify-write epilogue the other one keeps the DMMA pipe fed.
+constexpr int G3_BN = 64, G3_THREADS = 256;
+
+template <int BK, int STAGES>
+__global__ void __launch_bounds__(G3_THREADS, 2) gemm_nt_f64_v3_kernel(const GemmParams<double> p) {
+  constexpr int K8 = BK / 8;
+  constexpr int RB = K8 * 64;                     // doubles per 8-row block
+  constexpr int A_ELEMS = GM_BM * BK, B_ELEMS = G3_BN * BK;
+  constexpr int GPR = BK / 2;                     // granules per row
+  constexpr int ROWS_PER_PASS = G3_THREADS / GPR;
+  constexpr int A_PASSES = GM_BM / ROWS_PER_PASS, B_PASSES = G3_BN / ROWS_PER_PASS;
+  // tile mapping: p.tiles_n counts 64-wide column tiles here
+  int tm, tn;
+  tile_coords(blockIdx.x, p.tiles_m, p.tiles_n, tm, tn);
+  if (p.lower && tn * G3_BN >= (tm + 1) * GM_BM) return;
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;  // 4 x 2 warps; warp tile 32 x 32
+  extern __shared__ __align__(16) double gm_smem[];
+  double* As = gm_smem;
+  double* Bs = gm_smem + STAGES * A_ELEMS;
+
+  const int ld_row = tid / GPR, ld_g = tid % GPR;
+  const int ld_off = (ld_row >> 3) * RB + ((ld_g >> 2) * 32 + (ld_row & 7) * 4 + (ld_g & 3)) * 2;
+  const double* ld_a = p.A + (int64_t)b * p.a_bs + ((int64_t)tm * GM_BM + ld_row) * p.lda + ld_g * 2;
+  const double* ld_b = p.B + (int64_t)b * p.b_bs + ((int64_t)tn * G3_BN + ld_row) * p.ldb + ld_g * 2;
+  const int KT = (int)(p.K / BK);
+  int ld_kt = 0, ld_slot = 0;
+  auto load_next = [&]() {
+    if (ld_kt < KT) {
+      double* as = As + ld_slot * A_ELEMS + ld_off;
+      double* bs = Bs + ld_slot * B_ELEMS + ld_off;
+      const int64_t koff = (int64_t)ld_kt * BK;
+#pragma unroll
+      for (int i = 0; i < A_PASSES; ++i)
+        cp_async16(as + i * (ROWS_PER_PASS / 8) * RB, ld_a + (int64_t)i * ROWS_PER_PASS * p.lda + koff);
+#pragma unroll
+      for (int i = 0; i < B_PASSES; ++i)
+        cp_async16(bs + i * (ROWS_PER_PASS / 8) * RB, ld_b + (int64_t)i * ROWS_PER_PASS * p.ldb + koff);
+      ++ld_kt;
+      if (++ld_slot == STAGES) ld_slot = 0;
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) load_next();
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  int slot = 0;
+  const int frag_a = (wm * 4) * RB + lane * 2, frag_b = (wn * 4) * RB + lane * 2;
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    const double* as = As + slot * A_ELEMS + frag_a;
+    const double* bs = Bs + slot * B_ELEMS + frag_b;
+#pragma unroll
+    for (int k8 = 0; k8 < K8; ++k8) {
+      double2 a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const double2*>(as + i * RB + k8 * 64);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = *reinterpret_cast<const double2*>(bs + j * RB + k8 * 64);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, bb[j].x);
+      if (k8 == 0) load_next();
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, bb[j].y);
+    }
+    if (++slot == STAGES) slot = 0;
+  }
+  cp_async_wait<0>();
+
+  double* Cg = p.C + (int64_t)b * p.c_bs + ((int64_t)tm * GM_BM + wm * 32 + (lane >> 2)) * p.ldc +
+               (int64_t)tn * G3_BN + wn * 32 + 2 * (lane & 3);
+  const double alpha = p.alpha, beta = p.beta;
+  if (beta != 0.0) {
+    double2 old[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) old[i][j] = *reinterpret_cast<const double2*>(Cg + (int64_t)i * 8 * p.ldc + j * 8);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double2 v;
+        v.x = fma(alpha, acc[i][j][0], beta * old[i][j].x);
+        v.y = fma(alpha, acc[i][j][1], beta * old[i][j].y);
+        *reinterpret_cast<double2*>(Cg + (int64_t)i * 8 * p.ldc + j * 8) = v;
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<double2*>(Cg + (int64_t)i * 8 * p.ldc + j * 8) =
+            make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
+  }
+}
+
 // ---- fp32: register-tiled FFMA ------------------------------------------------------------------------
 constexpr int SG_BK = 16;
 
@@ -463,6 +575,35 @@ int gemm_nt_f64(int64_t M, int64_t N, int64_t K, double alpha, const double* A, 
   const int smem = 2 * GM_STAGES * GM_STAGE_ELEMS * (int)sizeof(double);
   const int n_groups = (tiles_m + 7) / 8;
   static const bool force_v1 = getenv("GPK_GEMM_V1") != nullptr;
+  static const int v3_mode = getenv("GPK_GEMM_V3") ? atoi(getenv("GPK_GEMM_V3")) : 1;  // 0 off, 1 BK32x2, 2 BK16x4
+  if (!force_v1 && v3_mode && K >= 512 && K % 32 == 0) {
+    GemmParams<double> p3{M, N, K, alpha, beta, A, lda, a_bs, B, ldb, b_bs, C, ldc, c_bs, lower, tiles_m,
+                          (int32_t)(N / G3_BN)};
+    constexpr int smem_a = (GM_BM + G3_BN) * 32 * 2 * (int)sizeof(double);  // BK = 32, 2 stages: 96 KB
+    constexpr int smem_b = (GM_BM + G3_BN) * 16 * 4 * (int)sizeof(double);  // BK = 16, 4 stages: 96 KB
+    static bool attr3_set = false;
+    if (!attr3_set) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_nt_f64_v3_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_nt_f64_v3_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
+      if (e != cudaSuccess) return -1000 - (int)e;
+      attr3_set = true;
+    }
+    dim3 grid3((unsigned)(p3.tiles_m * p3.tiles_n), (unsigned)batch);
+    if (g_prof.enabled) {
+      const double tn = (double)tiles_n, tmm = (double)tiles_m;
+      const double tiles = lower ? (tn * (tn + 1) / 2 + (tmm - tn) * tn) : tmm * tn;  // in 128 x 128 units
+      prof_begin(stream, tiles * 2.0 * GM_BM * GM_BN * (double)K * batch);
+    }
+    if (v3_mode == 2)
+      gemm_nt_f64_v3_kernel<16, 4><<<grid3, G3_THREADS, smem_b, stream>>>(p3);
+    else
+      gemm_nt_f64_v3_kernel<32, 2><<<grid3, G3_THREADS, smem_a, stream>>>(p3);
+    if (g_prof.enabled) prof_end(stream);
+    GPK_COUNT_LAUNCH();
+    GPK_CHECK_LAUNCH();
+    return 0;
+  }
   if (!force_v1 && K > 0 && (!lower || n_groups <= G2_MAX_GROUPS) && (int64_t)tiles_m * tiles_n * batch < (1ll << 30)) {
     static Gemm2Params q;  // large (group table): filled in place, passed by value at launch
     q.K = K; q.alpha = alpha; q.beta = beta; q.A = A; q.lda = lda; q.a_bs = a_bs; q.B = B; q.ldb = ldb; q.b_bs = b_bs;
