@@ -43,11 +43,35 @@ def make_inputs(seed, n=N_FULL):
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle restatement of the reference's numpy path
 # ----------------------------------------------------------------------------------------------------------------------
+SPEC = ("sum", ("stretched", ELL, ("eq",)), ("scaled", S2, ("delta",)))
+
+
 def oracle_logpdf(x, y):
     from oracle import gp_oracle as O
 
-    spec = ("sum", ("stretched", ELL, ("eq",)), ("scaled", S2, ("delta",)))
-    return float(O.fdd_logpdf(spec, x, None, y))
+    return float(O.fdd_logpdf(SPEC, x, None, y))
+
+
+def oracle_phases(x, y):
+    """One oracle logpdf, timed in its two phases: (kernel-matrix build [O(n^2)], Cholesky + solve + log-det [O(n^3)])."""
+    from oracle import gp_oracle as O
+
+    t0 = time.perf_counter()
+    K = O.kernel_matrix(SPEC, x)
+    t1 = time.perf_counter()
+    O.normal_logpdf(None, K, y)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm should still use every core BLAS can take."""
+    try:
+        import threadpoolctl
+
+        threadpoolctl.threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
 
 
 def cpu_threads():
@@ -65,49 +89,55 @@ def cost(n):
     return n**3 / 3.0 + n * n + n * n * (3 * D + 8)
 
 
-def time_oracle(n, reps=1):
-    x, y = make_inputs(2, n)
-    ts = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        oracle_logpdf(x, y)
-        ts.append(time.perf_counter() - t0)
-    return min(ts)
+def scale_to_full(t_build, t_rest, n):
+    """Extrapolate a sample at size n to n = 16384: the build scales with n^2, the factorisation with n^3."""
+    r = N_FULL / float(n)
+    return t_build * r**2 + t_rest * r**3
 
 
 def pick_sample_n(budget_s):
     """Largest n in {16384, 8192, 4096, 2048} whose predicted oracle time fits the per-step budget."""
-    t2k = time_oracle(2048, reps=2)  # also warms BLAS up
+    x, y = make_inputs(2, 2048)
+    oracle_phases(x, y)  # warm BLAS up
+    tb, tr = oracle_phases(x, y)
     for n in (16384, 8192, 4096, 2048):
-        pred = t2k * (0.5 * cost(n) / cost(2048) + 0.5 * (n / 2048.0) ** 2)  # mix of n^3 (BLAS-3) and n^2 (build)
-        if pred <= budget_s:
+        r = n / 2048.0
+        if tb * r**2 + tr * r**3 <= budget_s:
             return n
     return 2048
+
+
+def sample_text(steps, n_s, dt):
+    txt = f"{steps} x oracle logpdf at n={n_s}, d={D} ({dt:.3f} s each)"
+    if n_s != N_FULL:
+        txt += f", extrapolated to n={N_FULL}: kernel build x{(N_FULL / n_s) ** 2:.0f} (n^2), Cholesky+solve x{(N_FULL / n_s) ** 3:.0f} (n^3)"
+    return txt
 
 
 def reference_arm(args, rank):
     if rank != 0:
         return
+    use_all_host_threads()
     total_budget = 150.0
     n_s = pick_sample_n(total_budget / (args.steps + args.warmup))
     x, y = make_inputs(2, n_s)
     for _ in range(args.warmup):
-        oracle_logpdf(x, y)
-    t0 = time.perf_counter()
+        oracle_phases(x, y)
+    tb = tr = 0.0
     for _ in range(args.steps):
-        oracle_logpdf(x, y)
-    dt = (time.perf_counter() - t0) / args.steps
-    scale = cost(N_FULL) / cost(n_s)
-    value = 1.0 / (dt * scale)
-    sample = (f"{args.steps} x oracle logpdf at n={n_s}, d={D} ({dt:.3f} s each)"
-              + ("" if n_s == N_FULL else f", scaled to n={N_FULL} by the algorithmic flop ratio {scale:.1f}"))
+        b, r = oracle_phases(x, y)
+        tb += b / args.steps
+        tr += r / args.steps
+    t_full = scale_to_full(tb, tr, n_s)
+    value = 1.0 / t_full
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "EQ().stretch(2.0)+0.1*Delta(), n=16384, d=8, fp64: kernel build + Cholesky + logpdf",
                    "parallelism": "host cores (numpy/scipy oracle restatement of the reference path)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+                         "sample": sample_text(args.steps, n_s, tb + tr)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -263,13 +293,13 @@ def gpu_arm(args, rank, world, local_rank):
         lp_small = float(S.GP(kernel)(torch.as_tensor(xs, device=dev), None).logpdf(torch.as_tensor(ys, device=dev)))
         ref_small = oracle_logpdf(xs, ys)
         # bounded CPU baseline sample: the oracle at the largest n that fits ~25 s
+        use_all_host_threads()
         n_s = pick_sample_n(25.0)
-        dt = time_oracle(n_s)
-        scale = cost(N_FULL) / cost(n_s)
+        xs_, ys_ = make_inputs(2, n_s)
+        tb, tr = oracle_phases(xs_, ys_)
         cpu_baseline = {
-            "value": 1.0 / (dt * scale), "unit": UNIT, "cores": cpu_threads(), "kind": "port",
-            "sample": f"1 x oracle logpdf at n={n_s}, d={D} ({dt:.2f} s)"
-                      + ("" if n_s == N_FULL else f", scaled to n={N_FULL} by the algorithmic flop ratio {scale:.1f}"),
+            "value": 1.0 / scale_to_full(tb, tr, n_s), "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+            "sample": sample_text(1, n_s, tb + tr),
         }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

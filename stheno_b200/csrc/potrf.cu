@@ -236,6 +236,7 @@ trsm_leaf_tc_kernel(const T* __restrict__ L, int64_t ldl, int64_t l_bs, T* __res
   B += (int64_t)blockIdx.y * b_bs + (int64_t)blockIdx.x * TC_ROWS * ldb;
 
   // (1) L11 (lower part, zeros above) -> fragment-major shared memory; 8192 granules of 2 doubles
+#pragma unroll 4
   for (int gi = tid; gi < NB * NB / 2; gi += TC_THREADS) {
     const int c = gi >> 6, g = gi & 63;  // row c, granule g: columns 2g, 2g+1
     const int k = 2 * g;
@@ -254,19 +255,24 @@ trsm_leaf_tc_kernel(const T* __restrict__ L, int64_t ldl, int64_t l_bs, T* __res
   }
   __syncthreads();
   // (2) invert the eight diagonal blocks: warp d, lane c (< 16) solves L_d x = e_c by forward substitution
-  if (warp < 8 && lane < 16) {
-    const double* Lb = Ld + warp * 16 * 17;
-    double x[16];
+  //     (one reciprocal per diagonal entry, shared through the padding column of Ld; no divisions on the chain)
+  if (warp < 8) {
+    double* Lb = Ld + warp * 16 * 17;
+    if (lane < 16) Lb[lane * 17 + 16] = 1.0 / Lb[lane * 17 + lane];
+    __syncwarp();
+    if (lane < 16) {
+      double x[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      double s = (i == lane) ? 1.0 : 0.0;
+      for (int i = 0; i < 16; ++i) {
+        double s = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
-      for (int k = 0; k < 16; ++k)
-        if (k < i) s -= Lb[i * 17 + k] * x[k];
-      x[i] = (i >= lane) ? s / Lb[i * 17 + i] : 0.0;
+        for (int k = 0; k < 16; ++k)
+          if (k < i) s -= Lb[i * 17 + k] * x[k];
+        x[i] = (i >= lane) ? s * Lb[i * 17 + 16] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) Ls[frag_index(warp * 16 + i, warp * 16 + lane)] = x[i];
     }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) Ls[frag_index(warp * 16 + i, warp * 16 + lane)] = x[i];
   }
   __syncthreads();
 
@@ -334,172 +340,13 @@ static int launch_trsm_leaf_tc(const T* L, int64_t ldl, int64_t l_bs, T* B, int6
   return 0;
 }
 
-// ---- leaf Cholesky on the tensor cores: 128 x 128 block, 16 warps x 8 rows in DMMA accumulator fragments -----------
-// Blocked by 16 columns.  Per block: (1) the two warps owning the 16 x 16 diagonal block spill it to shared memory,
-// (2) ONE warp factorises it with register rows + shuffles (the only sequential part: 16 rsqrt steps) and inverts it,
-// (3) every warp below forms its panel rows  X = A inv(L_d)^T  with 6 DMMAs and publishes them as B-operand fragments,
-// (4) every warp applies the rank-16 update to its later column blocks with DMMAs straight from registers.
-// 3 block barriers per 16 columns (24 in total) instead of one per column (128), and the update flops run on the
-// tensor pipe.  T = storage type; the arithmetic is fp64 (cf. trsm_leaf_tc_kernel).
-__device__ __forceinline__ int frag16_index(int n, int k) {  // 16 x 16 operand, fragment-major
-  return (((n >> 3) * 2 + (k >> 3)) * 32 + (n & 7) * 4 + ((k & 7) >> 1)) * 2 + (k & 1);
-}
-
-// One warp: Cholesky of the 16 x 16 block in Dd AND its inverse in the same 16-step sweep.  Lane i keeps row i of the
-// block (-> L) and row i of W (starts as I -> L^-1) in registers; column j is broadcast by shuffles:
-//   pivot = rsqrt(a_jj);  l_ij = a_ij * pivot;  a_ik -= l_ij l_kj (k > j);   W_j *= pivot;  W_i -= l_ij W_j (i > j).
-// 17 shuffles and one rsqrt per column, no divisions, no shared-memory round trip.  Kept out of line so that the
-// 16 x 16 loops are unrolled once, not once per column block of the caller.
-__device__ __noinline__ int leaf16_factor_invert(const double* Dd, double* DinvS, double* diag16, int lane, int bad,
-                                                 int pivot_base) {
-  const int i = lane & 15;
-  double a[16], w[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    a[k] = Dd[i * 17 + k];
-    w[k] = (k == i) ? 1.0 : 0.0;
-  }
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const double djj = __shfl_sync(0xffffffffu, a[j], j);
-    if (!(djj > 0.0) && bad == 0) bad = pivot_base + j + 1;
-    const double inv = rsqrt(djj);
-    const double lcol = a[j] * inv;
-#pragma unroll
-    for (int k = j + 1; k < 16; ++k) {
-      const double v = __shfl_sync(0xffffffffu, lcol, k);
-      if (i >= k) a[k] -= lcol * v;
-    }
-#pragma unroll
-    for (int c = 0; c <= j; ++c) {
-      const double ws = w[c] * inv;
-      const double wj = __shfl_sync(0xffffffffu, ws, j);
-      if (i == j) w[c] = ws;
-      else if (i > j) w[c] -= lcol * wj;
-    }
-    a[j] = (i == j) ? djj * inv : lcol;
-  }
-  if (lane < 16) {
-    double dii = 0.0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      dii = (k == i) ? a[k] : dii;
-      DinvS[frag16_index(i, k)] = (k <= i) ? w[k] : 0.0;
-    }
-    diag16[i] = dii;
-  }
-  return bad;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-potrf_leaf_tc_kernel(T* __restrict__ A, int64_t lda, int64_t a_bs, T* __restrict__ logdet, int32_t* __restrict__ info,
-                     int32_t pivot_base) {
-  __shared__ __align__(16) double Xs[NB * 16];   // panel rows as B-operand fragments: [16 row blocks][2 k8][32][2]
-  __shared__ __align__(16) double DinvS[256];    // inverse of the diagonal block, fragment-major
-  __shared__ double Dd[16 * 17];
-  __shared__ double diag[NB];
-  __shared__ double red[16];
-  const int bidx = blockIdx.x;
-  A += (int64_t)bidx * a_bs;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r = lane >> 2, q = lane & 3;
-
-  double acc[16][2];
-  T* Aw = A + (int64_t)(warp * 8 + r) * lda + 2 * q;
-#pragma unroll
-  for (int cb = 0; cb < 16; ++cb) {
-    acc[cb][0] = (double)Aw[cb * 8];
-    acc[cb][1] = (double)Aw[cb * 8 + 1];
-  }
-  int bad = 0;
-
-#pragma unroll
-  for (int jb = 0; jb < 8; ++jb) {
-    // (1) diagonal block -> shared memory
-    if (warp == 2 * jb || warp == 2 * jb + 1) {
-      const int h = warp - 2 * jb;
-#pragma unroll
-      for (int cbl = 0; cbl < 2; ++cbl) {
-        Dd[(8 * h + r) * 17 + 8 * cbl + 2 * q] = acc[2 * jb + cbl][0];
-        Dd[(8 * h + r) * 17 + 8 * cbl + 2 * q + 1] = acc[2 * jb + cbl][1];
-      }
-    }
-    __syncthreads();
-    // (2) warp 0: 16 x 16 Cholesky (lane i holds row i) and its inverse
-    if (warp == 0) bad = leaf16_factor_invert(Dd, DinvS, diag + 16 * jb, lane, bad, pivot_base + 16 * jb);
-    __syncthreads();
-    // (3) panel rows of every warp at or below the diagonal block
-    double x[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-    if (warp >= 2 * jb) {
-#pragma unroll
-      for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-        for (int kg = 0; kg < 2; ++kg) {
-          if (kg > nb) continue;
-          const double2 b = *reinterpret_cast<const double2*>(DinvS + (nb * 2 + kg) * 64 + lane * 2);
-          dmma884(x[nb][0], x[nb][1], acc[2 * jb + kg][0], b.x);
-          dmma884(x[nb][0], x[nb][1], acc[2 * jb + kg][1], b.y);
-        }
-#pragma unroll
-      for (int nb = 0; nb < 2; ++nb) {
-        acc[2 * jb + nb][0] = x[nb][0];
-        acc[2 * jb + nb][1] = x[nb][1];
-        *reinterpret_cast<double2*>(Xs + (warp * 2 + nb) * 64 + lane * 2) = make_double2(x[nb][0], x[nb][1]);
-      }
-    }
-    __syncthreads();
-    // (4) rank-16 update of the later column blocks (lower part: column block <= own row block)
-    if (warp >= 2 * jb + 2) {
-#pragma unroll
-      for (int kg = 0; kg < 2; ++kg) {
-        const double nx0 = -x[kg][0], nx1 = -x[kg][1];
-#pragma unroll
-        for (int cb = 2 * jb + 2; cb < 16; ++cb) {
-          if (cb <= warp) {
-            const double2 b = *reinterpret_cast<const double2*>(Xs + (cb * 2 + kg) * 64 + lane * 2);
-            dmma884(acc[cb][0], acc[cb][1], nx0, b.x);
-            dmma884(acc[cb][0], acc[cb][1], nx1, b.y);
-          }
-        }
-      }
-    }
-  }
-
-  // write back the lower triangle
-  const int row = warp * 8 + r;
-#pragma unroll
-  for (int cb = 0; cb < 16; ++cb) {
-    const int col = cb * 8 + 2 * q;
-    if (col <= row) Aw[cb * 8] = (T)acc[cb][0];
-    if (col + 1 <= row) Aw[cb * 8 + 1] = (T)acc[cb][1];
-  }
-  if (warp == 0 && lane == 0 && bad) atomicCAS(info + bidx, 0, bad);
-  __syncthreads();
-  if (logdet != nullptr) {
-    double v = (tid < NB) ? log(diag[tid]) : 0.0;
-    v = warp_sum(v);
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    if (tid == 0) {
-      double sum = 0.0;
-#pragma unroll
-      for (int w = 0; w < 16; ++w) sum += red[w];
-      atomicAdd(logdet + bidx, (T)(2.0 * sum));
-    }
-  }
-}
-
 template <typename T>
 static int launch_potrf_leaf(T* A, int64_t lda, int64_t a_bs, T* logdet, int32_t* info, int32_t pivot_base,
                              int32_t batch, cudaStream_t stream) {
-  // Default: the register-tiled scalar leaf (46 us per 128 x 128 block).  The tensor-core leaf below is correct but
-  // its sequential 16 x 16 warp step is still slower in practice (72 us); GPK_TC_LEAF=1 selects it for tuning.
-  static const bool scalar_leaf = getenv("GPK_TC_LEAF") == nullptr;
-  if (scalar_leaf)
-    potrf_leaf_kernel<T><<<batch, 256, 0, stream>>>(A, lda, a_bs, logdet, info, pivot_base);
-  else
-    potrf_leaf_tc_kernel<T><<<batch, TC_THREADS, 0, stream>>>(A, lda, a_bs, logdet, info, pivot_base);
+  // (A DMMA-blocked leaf -- 16-column blocks, one warp factorising the 16 x 16 diagonal block with shuffles -- was
+  //  built and measured at 72-170 us per block against 46 us for this register-tiled kernel: a single warp cannot
+  //  retire the 16 x 16 step's dependent instruction stream fast enough.  See DESIGN.md section 8.)
+  potrf_leaf_kernel<T><<<batch, 256, 0, stream>>>(A, lda, a_bs, logdet, info, pivot_base);
   GPK_COUNT_LAUNCH();
   GPK_CHECK_LAUNCH();
   return 0;
