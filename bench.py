@@ -283,7 +283,7 @@ def gpu_arm(args, rank, world, local_rank):
         roofline = {
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": (achieved / peak) if achieved and peak > 0 else None, "traffic": None,
-            "kernel": "gpk::gemm_nt_f64_kernel (DMMA.8x8x4)",
+            "kernel": "gpk::gemm_nt_f64_v3_kernel<32,2> (DMMA.8x8x4; the K>=512 trailing SYRK updates of the Cholesky)",
             "peak_source": "fp64 DMMA issue peak measured in-run (gpk_probe_dmma_tflops); MEASURED_PEAKS.json has no fp64 entry",
             "launches_per_step": g_launches / prof_steps, "kernel_ms_per_step": g_ms / prof_steps,
             "whole_step_tflops": cost(N_FULL) / (ms / args.steps * 1e-3) / 1e12,

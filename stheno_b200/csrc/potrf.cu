@@ -345,7 +345,9 @@ static int launch_potrf_leaf(T* A, int64_t lda, int64_t a_bs, T* logdet, int32_t
                              int32_t batch, cudaStream_t stream) {
   // (A DMMA-blocked leaf -- 16-column blocks, one warp factorising the 16 x 16 diagonal block with shuffles -- was
   //  built and measured at 72-170 us per block against 46 us for this register-tiled kernel: a single warp cannot
-  //  retire the 16 x 16 step's dependent instruction stream fast enough.  See DESIGN.md section 8.)
+  //  retire the 16 x 16 step's dependent instruction stream fast enough.
+  //  A two-columns-per-barrier (rank-2) variant measured the same: the leaf is bound by its dependent
+  //  STS -> barrier -> LDS -> rsqrt -> DMUL -> DFMA chain, not by the barrier count or the fp64 pipe.)
   potrf_leaf_kernel<T><<<batch, 256, 0, stream>>>(A, lda, a_bs, logdet, info, pivot_base);
   GPK_COUNT_LAUNCH();
   GPK_CHECK_LAUNCH();
