@@ -388,3 +388,50 @@ def test_named_gps_and_default_measure(S):
     assert h.measure is not m
     with pytest.raises(AssertionError):
         f + h
+
+
+def test_normal_with_explicit_variance(S):
+    # tests/test_random.py:185-192 : logpdf against SciPy's formula via the oracle, 10 right-hand sides
+    rng = np.random.default_rng(20)
+    a = rng.standard_normal((30, 30))
+    var = a @ a.T + 0.5 * np.eye(30)
+    mean = rng.standard_normal((30, 1))
+    x = rng.standard_normal((30, 10))
+    dist = S.Normal(mean, var)
+    approx(dist.logpdf(x), O.normal_logpdf(mean, var, x), rtol=1e-9)
+    assert np.ndim(dist.logpdf(x[:, 0])) == 0
+    assert dist.dim == 30 and dist.dtype == torch.float64
+    approx(dist.m2, var + mean @ mean.T)
+    # Diagonal variance keeps its structure
+    dn = S.Normal(S.Diagonal(S._util.to_dev(np.full(30, 2.0))))
+    approx(dn.logpdf(x[:, :3]), O.normal_logpdf(None, 2.0 * np.eye(30), x[:, :3]), rtol=1e-12)
+
+
+def test_float32_and_batched_posterior(S):
+    rng = np.random.default_rng(21)
+    S.B.epsilon = 1e-6
+    x = rng.standard_normal((3, 60, 2)).astype(np.float32)
+    y = rng.standard_normal((3, 60, 1)).astype(np.float32)
+    xs = rng.standard_normal((3, 9, 2)).astype(np.float32)
+    noise = rng.uniform(0.2, 0.4, (3, 60)).astype(np.float32)
+    f = S.GP(S.Matern52().stretch(1.2))
+    post = f | (f(x, noise), y)
+    mean, var = post(xs).marginals()
+    assert mean.shape == (3, 9) and mean.dtype == np.float32
+    for b in range(3):
+        mref, vref = O.posterior_marginals(("stretched", 1.2, ("matern52",)), x[b].astype(np.float64),
+                                           noise[b].astype(np.float64), y[b].astype(np.float64),
+                                           xs[b].astype(np.float64), eps=1e-6)
+        approx(mean[b], mref, rtol=1e-3, atol=1e-4)
+        approx(var[b], vref, rtol=1e-3, atol=1e-4)
+
+
+def test_kernel_limits_are_reported(S):
+    # more product terms than the descriptor holds -> a clear error, not a wrong answer
+    from stheno_b200._lib import GpkError
+
+    k = S.EQ()
+    for i in range(9):
+        k = k + (i + 2.0) * S.Matern32().stretch(float(i + 2))
+    with pytest.raises(GpkError):
+        S.GP(k)(np.linspace(0, 1, 5)).var.mat
