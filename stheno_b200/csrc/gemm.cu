@@ -675,12 +675,19 @@ int gemm_nt_f64(int64_t M, int64_t N, int64_t K, double alpha, const double* A, 
   return 0;
 }
 
+int gemm_nt_f32_tc(int64_t, int64_t, int64_t, float, const float*, int64_t, int64_t, const float*, int64_t, int64_t, float,
+                   float*, int64_t, int64_t, int32_t, int32_t, cudaStream_t);  // gemm_tc32.cu (tcgen05 3xTF32)
+
 int gemm_nt_f32(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, int64_t a_bs,
                 const float* B, int64_t ldb, int64_t b_bs, float beta, float* C, int64_t ldc, int64_t c_bs,
                 int32_t lower, int32_t batch, cudaStream_t stream) {
   int rc = check_gemm_args<float>(M, N, K, A, lda, B, ldb, C, ldc, batch);
   if (rc) return rc;
   if (M == 0 || N == 0) return 0;
+  // tensor-core path (tcgen05 + TMEM + TMA, 3xTF32) when the shape allows it; FFMA kernel otherwise
+  rc = gemm_nt_f32_tc(M, N, K, alpha, A, lda, a_bs, B, ldb, b_bs, beta, C, ldc, c_bs, lower, batch, stream);
+  if (rc < 0) return rc;
+  if (rc == 1) return 0;
   GemmParams<float> p{M, N, K, alpha, beta, A, lda, a_bs, B, ldb, b_bs, C, ldc, c_bs, lower,
                       (int32_t)(M / GM_BM), (int32_t)(N / GM_BN)};
   dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch);
