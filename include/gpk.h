@@ -134,6 +134,13 @@ int gpk_potrf_f64(double* A, int64_t lda, int64_t a_bstride, int64_t n_pad, int6
 int gpk_potrf_f32(float* A, int64_t lda, int64_t a_bstride, int64_t n_pad, int64_t extra_rows, float* logdet,
                   int32_t* info, int32_t batch, void* stream);
 
+/* Opt-in mixed precision (BASELINE north_star: "tf32/bf16 where the user opts in"): same factorisation, but the
+ * K >= 128 trailing updates of the fp64 matrix are formed from an fp32 copy of the panel by the tcgen05 3xTF32 kernel
+ * (fp32-level products, fp64 accumulation into the matrix).  `ws`: float workspace of >= (n_pad + extra_rows) * 512
+ * elements.  Results agree with gpk_potrf_f64 to ~1e-6 relative, NOT to the 1e-10 parity bar: never the default. */
+int gpk_potrf_f64_tf32x3(double* A, int64_t lda, int64_t a_bstride, int64_t n_pad, int64_t extra_rows, double* logdet,
+                         int32_t* info, int32_t batch, float* ws, int64_t ws_elems, void* stream);
+
 /* K3: X * L^T = B  in place (B: rows x n_pad, rows a multiple of 64; L: n_pad x n_pad lower).
  * Row r of the result is (L^-1 b_r)^T.  Replaces B.solve(L, .) / B.iqf:  stheno/model/observations.py:301 and
  * the PosteriorMean / PosteriorKernel evaluation behind observations.py:143-168. */

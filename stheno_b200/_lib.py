@@ -56,6 +56,7 @@ _PLAIN = {
     "gpk_probe_dmma_tflops": ([], c_double),
     "gpk_launch_count": ([], _i64),
     "gpk_launch_count_reset": ([], None),
+    "gpk_potrf_f64_tf32x3": ([_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _i32, _ptr, _i64, _ptr], c_int32),
     "gpk_gemm_profile_enable": ([_i32], None),
     "gpk_gemm_profile_read": ([POINTER(c_double), POINTER(c_double), POINTER(_i64)], c_int32),
 }

@@ -30,7 +30,7 @@ constexpr int TC_GEMM_THREADS = 192;
 
 struct TcParams {
   float alpha, beta;
-  float* C;
+  void* C;  // float* or double* (CT of the kernel)
   int64_t ldc, c_bs;
   int32_t K, lower, tiles_m, tiles_n;
 };
@@ -87,6 +87,9 @@ __device__ __forceinline__ float4 tf32_low_part(float4 v) {
   return lo;
 }
 
+// CT = type of C: float (fp32 problems) or double (opt-in mixed precision: fp64 matrix, fp32 operands -- the
+// "tf32 where the user opts in" trailing update of the fp64 Cholesky).
+template <typename CT>
 __global__ void __launch_bounds__(TC_GEMM_THREADS, 1)
 gemm_nt_f32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                       const TcParams p) {
@@ -183,7 +186,7 @@ gemm_nt_f32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
     const int lane_group = warp & 3;  // a warp may only touch TMEM lanes 32 * (warp % 4) .. + 31
     const int row = lane_group * 32 + lane;
-    float* Crow = p.C + (int64_t)b * p.c_bs + ((int64_t)tm * TC_BM + row) * p.ldc + (int64_t)tn * TC_BN;
+    CT* Crow = static_cast<CT*>(p.C) + (int64_t)b * p.c_bs + ((int64_t)tm * TC_BM + row) * p.ldc + (int64_t)tn * TC_BN;
     const float alpha = p.alpha, beta = p.beta;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
@@ -198,22 +201,39 @@ gemm_nt_f32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
             "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::);
-      float4* cp = reinterpret_cast<float4*>(Crow + c * 32);
+      if (sizeof(CT) == 4) {
+        float4* cp = reinterpret_cast<float4*>(Crow + c * 32);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 v;
-        v.x = alpha * __uint_as_float(r[4 * j + 0]);
-        v.y = alpha * __uint_as_float(r[4 * j + 1]);
-        v.z = alpha * __uint_as_float(r[4 * j + 2]);
-        v.w = alpha * __uint_as_float(r[4 * j + 3]);
-        if (beta != 0.f) {
-          const float4 o = cp[j];
-          v.x = fmaf(beta, o.x, v.x);
-          v.y = fmaf(beta, o.y, v.y);
-          v.z = fmaf(beta, o.z, v.z);
-          v.w = fmaf(beta, o.w, v.w);
+        for (int j = 0; j < 8; ++j) {
+          float4 v;
+          v.x = alpha * __uint_as_float(r[4 * j + 0]);
+          v.y = alpha * __uint_as_float(r[4 * j + 1]);
+          v.z = alpha * __uint_as_float(r[4 * j + 2]);
+          v.w = alpha * __uint_as_float(r[4 * j + 3]);
+          if (beta != 0.f) {
+            const float4 o = cp[j];
+            v.x = fmaf(beta, o.x, v.x);
+            v.y = fmaf(beta, o.y, v.y);
+            v.z = fmaf(beta, o.z, v.z);
+            v.w = fmaf(beta, o.w, v.w);
+          }
+          cp[j] = v;
         }
-        cp[j] = v;
+      } else {
+        double2* cp = reinterpret_cast<double2*>(Crow + c * 32);
+        const double da = (double)alpha, db = (double)beta;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          double2 v;
+          v.x = da * (double)__uint_as_float(r[2 * j + 0]);
+          v.y = da * (double)__uint_as_float(r[2 * j + 1]);
+          if (beta != 0.f) {
+            const double2 o = cp[j];
+            v.x = fma(db, o.x, v.x);
+            v.y = fma(db, o.y, v.y);
+          }
+          cp[j] = v;
+        }
       }
     }
   }
@@ -249,6 +269,28 @@ static bool make_map(CUtensorMap* m, const float* base, int64_t K, int64_t rows,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+template <typename CT>
+static int launch_tc(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, int64_t a_bs,
+                     const float* B, int64_t ldb, int64_t b_bs, float beta, CT* C, int64_t ldc, int64_t c_bs, int32_t lower,
+                     int32_t batch, cudaStream_t stream) {
+  CUtensorMap mA, mB;
+  if (!make_map(&mA, A, K, M, lda, a_bs, batch) || !make_map(&mB, B, K, N, ldb, b_bs, batch)) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(gemm_nt_f32_tc_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    if (e != cudaSuccess) return -1000 - (int)e;
+    attr_set = true;
+  }
+  TcParams p{alpha, beta, C, ldc, c_bs, (int32_t)K, lower, (int32_t)(M / TC_BM), (int32_t)(N / TC_BN)};
+  dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch);
+  gemm_nt_f32_tc_kernel<CT><<<grid, TC_GEMM_THREADS, TC_SMEM_BYTES, stream>>>(mA, mB, p);
+  GPK_COUNT_LAUNCH();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return -1000 - (int)e;
+  return 1;
+}
+
 // returns 1 if the problem was launched on the tcgen05 path, 0 if the caller should use the FFMA kernel, < 0 on error
 int gemm_nt_f32_tc(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, int64_t a_bs, const float* B,
                    int64_t ldb, int64_t b_bs, float beta, float* C, int64_t ldc, int64_t c_bs, int32_t lower,
@@ -257,21 +299,33 @@ int gemm_nt_f32_tc(int64_t M, int64_t N, int64_t K, float alpha, const float* A,
   if (disabled || K < 128 || K % TC_BK || M % TC_BM || N % TC_BN) return 0;
   if (lda % 4 || ldb % 4 || ldc % 4 || (batch > 1 && (a_bs % 4 || b_bs % 4))) return 0;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) % 16) return 0;
-  CUtensorMap mA, mB;
-  if (!make_map(&mA, A, K, M, lda, a_bs, batch) || !make_map(&mB, B, K, N, ldb, b_bs, batch)) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_nt_f32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-    if (e != cudaSuccess) return -1000 - (int)e;
-    attr_set = true;
-  }
-  TcParams p{alpha, beta, C, ldc, c_bs, (int32_t)K, lower, (int32_t)(M / TC_BM), (int32_t)(N / TC_BN)};
-  dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch);
-  gemm_nt_f32_tc_kernel<<<grid, TC_GEMM_THREADS, TC_SMEM_BYTES, stream>>>(mA, mB, p);
+  return launch_tc<float>(M, N, K, alpha, A, lda, a_bs, B, ldb, b_bs, beta, C, ldc, c_bs, lower, batch, stream);
+}
+
+// ---- opt-in mixed precision for the fp64 Cholesky: trailing update C(fp64) -= P P^T with P rounded to fp32 and the
+// product formed by the 3xTF32 tensor-core kernel above (north_star: "tf32/bf16 where the user opts in") ----------------
+__global__ void f64_to_f32_panel_kernel(const double* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t rows,
+                                        int64_t K) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * K) return;
+  const int64_t r = idx / K, k = idx - r * K;
+  dst[idx] = (float)src[r * lds + k];
+}
+
+// C[M x N] (lower tiles) -= P[0:M] P[0:N]^T, P = fp64 panel (M x K, ld = ldp) converted into ws (M x K floats).
+int syrk_f64_tf32x3(int64_t M, int64_t N, int64_t K, const float* ws_rows, double* C, int64_t ldc, cudaStream_t stream) {
+  if (K % TC_BK || M % TC_BM || N % TC_BN || K < 128) return GPK_ERR_ARG;
+  const int rc = launch_tc<double>(M, N, K, -1.0f, ws_rows, K, 0, ws_rows, K, 0, 1.0f, C, ldc, 0, 1, 1, stream);
+  return rc == 1 ? 0 : (rc < 0 ? rc : GPK_ERR_UNSUPPORTED);
+}
+
+int convert_panel_f32(const double* P, int64_t ldp, int64_t rows, int64_t K, float* ws, cudaStream_t stream) {
+  const int64_t total = rows * K;
+  if (total == 0) return 0;
+  f64_to_f32_panel_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(P, ldp, ws, rows, K);
   GPK_COUNT_LAUNCH();
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return -1000 - (int)e;
-  return 1;
+  return e == cudaSuccess ? 0 : -1000 - (int)e;
 }
 
 }  // namespace gpk

@@ -439,9 +439,30 @@ static int factor_panel(T* A, int64_t lda, int64_t a_bs, int64_t R, int64_t kb, 
 // (a) the columns of panel i+1 and (b) everything to the right of it; as soon as (a) is done the latency-bound
 // factorisation of panel i+1 runs on a high-priority side stream while the tensor-core-bound update (b) keeps the
 // SMs busy on the caller's stream.
+int syrk_f64_tf32x3(int64_t, int64_t, int64_t, const float*, double*, int64_t, cudaStream_t);  // gemm_tc32.cu
+int convert_panel_f32(const double*, int64_t, int64_t, int64_t, float*, cudaStream_t);
+
+// trailing update C -= P P^T (lower tiles): fp64 DMMA by default; with a float workspace `ws` holding the fp32 copy of
+// the panel rows starting at `ws_row0`, the opt-in 3xTF32 tensor-core product.
+template <typename T>
+static int trailing_update(int64_t M, int64_t N, int64_t K, const T* P, int64_t lda, int64_t a_bs, T* C, int32_t batch,
+                           const float* ws_rows, cudaStream_t stream) {
+  return gemm_nt(M, N, K, T(-1), P, lda, a_bs, P, lda, a_bs, T(1), C, lda, a_bs, 1, batch, stream);
+}
+template <>
+int trailing_update<double>(int64_t M, int64_t N, int64_t K, const double* P, int64_t lda, int64_t a_bs, double* C,
+                            int32_t batch, const float* ws_rows, cudaStream_t stream) {
+  if (ws_rows != nullptr) return syrk_f64_tf32x3(M, N, K, ws_rows, C, lda, stream);
+  return gemm_nt(M, N, K, -1.0, P, lda, a_bs, P, lda, a_bs, 1.0, C, lda, a_bs, 1, batch, stream);
+}
+static int convert_panel(const double* P, int64_t ldp, int64_t rows, int64_t K, float* ws, cudaStream_t s) {
+  return convert_panel_f32(P, ldp, rows, K, ws, s);
+}
+static int convert_panel(const float*, int64_t, int64_t, int64_t, float*, cudaStream_t) { return 0; }
+
 template <typename T>
 static int potrf_driver(T* A, int64_t lda, int64_t a_bs, int64_t n_pad, int64_t extra_rows, T* logdet, int32_t* info,
-                        int32_t batch, cudaStream_t stream) {
+                        int32_t batch, cudaStream_t stream, float* ws = nullptr, int64_t ws_elems = 0) {
   if (!A || n_pad < 0 || extra_rows < 0 || batch < 1 || !info) return GPK_ERR_ARG;
   if (n_pad % NB || extra_rows % NB || lda < n_pad) return GPK_ERR_ARG;
   if (lda % (16 / sizeof(T)) || reinterpret_cast<uintptr_t>(A) % 16) return GPK_ERR_ALIGN;
@@ -457,9 +478,13 @@ static int potrf_driver(T* A, int64_t lda, int64_t a_bs, int64_t n_pad, int64_t 
     const int64_t ke = kb + NB_OUTER;                                   // panel [kb, ke) is factorised
     const int64_t ke2 = (ke + NB_OUTER < n_pad) ? ke + NB_OUTER : n_pad;  // next panel [ke, ke2)
     const int64_t K = ke - kb;
+    // opt-in mixed precision: fp32 copy of the panel rows [ke, R) for the tensor-core (3xTF32) trailing update
+    const bool mixed = ws != nullptr && sizeof(T) == 8 && batch == 1 && K % 32 == 0 && K >= 128 &&
+                       ws_elems >= (R - ke) * K;
+    if (mixed && (rc = convert_panel(A + ke * lda + kb, lda, R - ke, K, ws, stream))) return rc;
     // (a) update the next panel's columns
-    if ((rc = gemm_nt(R - ke, ke2 - ke, K, T(-1), A + ke * lda + kb, lda, a_bs, A + ke * lda + kb, lda, a_bs, T(1),
-                      A + ke * lda + ke, lda, a_bs, 1, batch, stream)))
+    if ((rc = trailing_update<T>(R - ke, ke2 - ke, K, A + ke * lda + kb, lda, a_bs, A + ke * lda + ke, batch,
+                                 mixed ? ws : nullptr, stream)))
       return rc;
     const bool more = ke2 < n_pad;
     if (use_la && more) {
@@ -470,8 +495,8 @@ static int potrf_driver(T* A, int64_t lda, int64_t a_bs, int64_t n_pad, int64_t 
     }
     // (b) update everything to the right of the next panel
     if (more) {
-      if ((rc = gemm_nt(R - ke2, n_pad - ke2, K, T(-1), A + ke2 * lda + kb, lda, a_bs, A + ke2 * lda + kb, lda, a_bs,
-                        T(1), A + ke2 * lda + ke2, lda, a_bs, 1, batch, stream)))
+      if ((rc = trailing_update<T>(R - ke2, n_pad - ke2, K, A + ke2 * lda + kb, lda, a_bs, A + ke2 * lda + ke2, batch,
+                                   mixed ? ws + (ke2 - ke) * K : nullptr, stream)))
         return rc;
     }
     if (use_la && more) {
@@ -557,6 +582,11 @@ extern "C" {
 int gpk_potrf_f64(double* A, int64_t lda, int64_t a_bstride, int64_t n_pad, int64_t extra_rows, double* logdet,
                   int32_t* info, int32_t batch, void* stream) {
   return gpk::potrf_driver<double>(A, lda, a_bstride, n_pad, extra_rows, logdet, info, batch, (cudaStream_t)stream);
+}
+int gpk_potrf_f64_tf32x3(double* A, int64_t lda, int64_t a_bstride, int64_t n_pad, int64_t extra_rows, double* logdet,
+                         int32_t* info, int32_t batch, float* ws, int64_t ws_elems, void* stream) {
+  return gpk::potrf_driver<double>(A, lda, a_bstride, n_pad, extra_rows, logdet, info, batch, (cudaStream_t)stream, ws,
+                                   ws_elems);
 }
 int gpk_potrf_f32(float* A, int64_t lda, int64_t a_bstride, int64_t n_pad, int64_t extra_rows, float* logdet,
                   int32_t* info, int32_t batch, void* stream) {

@@ -342,6 +342,15 @@ def _potrf(W, n, n_pad, extra, k):
     B = W.shape[0]
     logdet = torch.zeros(B, device=W.device, dtype=W.dtype)
     info = torch.zeros(B, device=W.device, dtype=torch.int32)
+    from . import B as _Bns
+
+    if W.dtype == torch.float64 and B == 1 and getattr(_Bns, "precision", "fp64") == "tf32x3" and n_pad > 512:
+        # opt-in mixed precision: trailing updates on the tcgen05 tensor cores (3xTF32) from an fp32 panel copy
+        ws = torch.empty((n_pad + extra) * 512, device=W.device, dtype=torch.float32)
+        rc = _lib.load().gpk_potrf_f64_tf32x3(_ptr(W), W.stride(1), W.stride(0), n_pad, extra, _ptr(logdet), _ptr(info),
+                                              B, _ptr(ws), ws.numel(), _stream())
+        check(rc, "gpk_potrf_f64_tf32x3")
+        return Chol(W, n, k, logdet, info)
     rc = _fn("gpk_potrf", W.dtype)(_ptr(W), W.stride(1), W.stride(0), n_pad, extra, _ptr(logdet), _ptr(info), B,
                                    _stream())
     check(rc, "gpk_potrf")

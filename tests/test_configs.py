@@ -135,3 +135,25 @@ def test_config5_golden_reduced(S):
     n = len(x)
     pairs = [(fs[i](x, 0.5), y[i * n:(i + 1) * n]) for i in range(4)]
     assert rel(m.logpdf(*pairs), g["logpdf"]) < 1e-10
+
+
+def test_opt_in_tf32x3_trailing_update(S):
+    """BASELINE north_star: "tf32/bf16 where the user opts in".  B.precision = "tf32x3" moves the K >= 128 trailing updates of
+    the fp64 Cholesky to the tcgen05 tensor cores (fp32 panel copy, 3xTF32 products).  It is an accuracy/speed trade:
+    fp32-level agreement, not the 1e-10 parity bar -- hence opt-in."""
+    rng = np.random.default_rng(7)
+    n, d = 3000, 8
+    x = torch.as_tensor(rng.standard_normal((n, d)), device="cuda")
+    y = torch.as_tensor(rng.standard_normal(n), device="cuda")
+    f = S.GP(S.EQ().stretch(2.0))
+    ref = f(x, 0.1).logpdf(y)
+    try:
+        S.B.precision = "tf32x3"
+        fast = f(x, 0.1).logpdf(y)
+    finally:
+        S.B.precision = "fp64"
+    rel = abs((fast - ref).item() / ref.item())
+    assert rel < 1e-4, rel
+    assert rel > 0  # it really took the other path
+    again = f(x, 0.1).logpdf(y)
+    assert again.item() == ref.item()
