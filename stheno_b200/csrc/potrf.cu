@@ -407,8 +407,13 @@ struct Lookahead {
 };
 
 static Lookahead& lookahead() {
-  static thread_local Lookahead la;  // thread_local: per host thread, tied to the thread's current device
-  return la;
+  // one side stream per (host thread, device): the stream must live on the device the caller's stream belongs to
+  static thread_local Lookahead* la[64] = {nullptr};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev = (dev < 0 || dev >= 64) ? 0 : dev;
+  if (la[dev] == nullptr) la[dev] = new Lookahead();
+  return *la[dev];
 }
 
 // Factorise the outer panel [kb, ke): leaf Cholesky, leaf TRSM of all rows below, rank-128 update of the rest of

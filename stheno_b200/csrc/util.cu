@@ -63,17 +63,18 @@ __global__ void pad_copy_kernel(const T* __restrict__ src, int64_t lds, int64_t 
                                 T* __restrict__ dst, int64_t ldd, int64_t d_bs, int64_t rows_pad, int64_t cols_pad,
                                 T diag_add, int32_t pad_identity) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t r = blockIdx.y;
   const int b = blockIdx.z;
-  if (c >= cols_pad || r >= rows_pad) return;
-  T v;
-  if (r < rows && c < cols) {
-    v = src[(int64_t)b * s_bs + r * lds + c];
-    if (r == c) v += diag_add;
-  } else {
-    v = (pad_identity && r == c) ? T(1) : T(0);
+  if (c >= cols_pad) return;
+  for (int64_t r = blockIdx.y; r < rows_pad; r += gridDim.y) {  // grid.y is capped at 65535
+    T v;
+    if (r < rows && c < cols) {
+      v = src[(int64_t)b * s_bs + r * lds + c];
+      if (r == c) v += diag_add;
+    } else {
+      v = (pad_identity && r == c) ? T(1) : T(0);
+    }
+    dst[(int64_t)b * d_bs + r * ldd + c] = v;
   }
-  dst[(int64_t)b * d_bs + r * ldd + c] = v;
 }
 
 // mirror lower -> upper, 32 x 32 tiles through shared memory
@@ -161,8 +162,7 @@ __global__ void dmma_probe_kernel(double* out, int iters, double a, double b) {
                          int32_t pad_identity, int32_t batch, void* stream) {                                          \
     if (!dst || rows < 0 || cols < 0 || rows_pad < rows || cols_pad < cols || batch < 1) return GPK_ERR_ARG;           \
     if (rows_pad == 0 || cols_pad == 0) return 0;                                                                      \
-    if (rows_pad > 65535 * 1 && rows_pad > 2147483647LL) return GPK_ERR_UNSUPPORTED;                                   \
-    dim3 grid((unsigned)((cols_pad + 255) / 256), (unsigned)rows_pad, (unsigned)batch);                                \
+    dim3 grid((unsigned)((cols_pad + 255) / 256), (unsigned)(rows_pad < 65535 ? rows_pad : 65535), (unsigned)batch);   \
     gpk::pad_copy_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(src, lds, s_bstride, rows, cols, dst, ldd,         \
                                                                    d_bstride, rows_pad, cols_pad, (T)diag_add,         \
                                                                    pad_identity);                                      \
