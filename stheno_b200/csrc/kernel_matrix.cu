@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(KM_THREADS) kernel_matrix_kernel(const KmParam
     for (int f = p.desc.term_begin[t]; f < p.desc.term_begin[t + 1]; ++f) {
       const int kind = p.desc.fac_kind[f];
       const int g = p.desc.fac_group[f];
-      if (g != last_g && kind != GPK_ONE && !(kind == GPK_DELTA && same_obj)) {
+      if ((g != last_g || kind == GPK_LINEAR) && kind != GPK_ONE && !(kind == GPK_DELTA && same_obj)) {
         last_g = g;
         const T* xr_ = xs + ((size_t)g * KM_TILE + ty * 4) * d;
         const T* yc_ = yt + (size_t)g * d * (KM_TILE + 1) + tx;
@@ -187,20 +187,35 @@ __global__ void __launch_bounds__(KM_THREADS) kernel_matrix_kernel(const KmParam
             d2[i][j] = T(0);
             dt[i][j] = T(0);
           }
-        for (int k = 0; k < d; ++k) {
-          T xv[4], yv[4];
+        if (kind == GPK_LINEAR) {  // inner products only for the Linear kernel (warp-uniform branch)
+          for (int k = 0; k < d; ++k) {
+            T xv[4], yv[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) xv[i] = xr_[i * d + k];
+            for (int i = 0; i < 4; ++i) xv[i] = xr_[i * d + k];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) yv[j] = yc_[(size_t)k * (KM_TILE + 1) + 16 * j];
+            for (int j = 0; j < 4; ++j) yv[j] = yc_[(size_t)k * (KM_TILE + 1) + 16 * j];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              T df = xv[i] - yv[j];
-              d2[i][j] = fma(df, df, d2[i][j]);
-              dt[i][j] = fma(xv[i], yv[j], dt[i][j]);
-            }
+              for (int j = 0; j < 4; ++j) dt[i][j] = fma(xv[i], yv[j], dt[i][j]);
+          }
+          last_g = -1;  // d2 was not formed: a following distance-based factor of the same group recomputes
+        } else {
+#pragma unroll 2
+          for (int k = 0; k < d; ++k) {
+            T xv[4], yv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xv[i] = xr_[i * d + k];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) yv[j] = yc_[(size_t)k * (KM_TILE + 1) + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                T df = xv[i] - yv[j];
+                d2[i][j] = fma(df, df, d2[i][j]);
+              }
+          }
         }
       }
 #pragma unroll

@@ -435,3 +435,69 @@ def test_kernel_limits_are_reported(S):
         k = k + (i + 2.0) * S.Matern32().stretch(float(i + 2))
     with pytest.raises(GpkError):
         S.GP(k)(np.linspace(0, 1, 5)).var.mat
+
+
+def test_combine_and_multi_fdd_observations(S):
+    # tests/model/test_observations.py:8-41 : joint of independent FDDs = concat mean + block-diag var
+    rng = np.random.default_rng(30)
+    m = S.Measure()
+    f1 = S.GP(lambda t: t, S.EQ(), measure=m)
+    f2 = S.GP(2.0 * S.Matern32(), measure=m)
+    x1, x2 = rng.standard_normal((4, 1)), rng.standard_normal((3, 1))
+    joint = S.combine(f1(x1, 0.1), f2(x2, np.array([0.2, 0.3, 0.4])))
+    K = np.zeros((7, 7))
+    K[:4, :4] = O.kernel_matrix(("eq",), x1) + 0.1 * np.eye(4)
+    K[4:, 4:] = 2.0 * O.kernel_matrix(("matern32",), x2) + np.diag([0.2, 0.3, 0.4])
+    approx(S.B.dense(joint.var), K, rtol=1e-10, atol=1e-12)
+    approx(joint.mean, np.concatenate([x1, np.zeros((3, 1))]))
+    # sparse observations with inducing points in two processes
+    y1, y2 = rng.standard_normal(4), rng.standard_normal(3)
+    obs = S.PseudoObs((f1(x1), f2(x2)), (f1(x1, 0.1), y1), (f2(x2, 0.2), y2))
+    exact = m.logpdf((f1(x1, 0.1), y1), (f2(x2, 0.2), y2))
+    approx(obs.elbo(m), exact, atol=1e-5, rtol=0)
+
+
+def test_fdd_take_and_mask_errors(S):
+    f = S.GP(S.EQ())
+    x = np.linspace(0, 1, 6)
+    fd = f(x, np.arange(1.0, 7.0))
+    mask = np.array([True, False, True, True, False, True])
+    sub = fd.take(mask)
+    approx(S.B.dense(sub.var), O.kernel_matrix(("eq",), x[mask]) + np.diag(np.arange(1.0, 7.0)[mask]))
+    with pytest.raises(AssertionError):
+        fd.take(np.array([0, 2]))
+
+
+def test_normal_arithmetic_and_lazy_contracts(S):
+    # tests/test_random.py:97-158 : laziness contracts of mean_var / marginals
+    calls = {"mean": 0, "var": 0, "mv": 0, "mvd": 0}
+    dev = S._util._device_fn()
+
+    def mean():
+        calls["mean"] += 1
+        return torch.ones(3, 1, dtype=torch.float64, device=dev)
+
+    def var():
+        calls["var"] += 1
+        return torch.eye(3, dtype=torch.float64, device=dev)
+
+    def mv():
+        calls["mv"] += 1
+        return mean(), var()
+
+    def mvd():
+        calls["mvd"] += 1
+        return torch.ones(3, 1, dtype=torch.float64, device=dev), torch.ones(3, dtype=torch.float64, device=dev)
+
+    d = S.Normal(mean, var, mean_var=mv, mean_var_diag=mvd)
+    m, v = d.mean_var
+    assert calls["mv"] == 1
+    d2 = S.Normal(mean, var, mean_var=mv, mean_var_diag=mvd)
+    mm, vv = d2.marginals()
+    assert calls["mvd"] == 1 and mm.shape == (3,) and vv.shape == (3,)
+    scaled = S.Normal(np.ones((2, 1)), np.eye(2)) * 3.0
+    approx(S.B.dense(scaled.var), 9 * np.eye(2))
+    a = np.array([[1.0, 2.0]])
+    lm = S.Normal(np.ones((2, 1)), np.eye(2)).lmatmul(a)
+    approx(S.B.dense(lm.var), a @ a.T)
+    approx(lm.mean, a @ np.ones((2, 1)))
