@@ -487,26 +487,32 @@ static int potrf_driver(T* A, int64_t lda, int64_t a_bs, int64_t n_pad, int64_t 
     const bool mixed = ws != nullptr && sizeof(T) == 8 && batch == 1 && K % 32 == 0 && K >= 128 &&
                        ws_elems >= (R - ke) * K;
     if (mixed && (rc = convert_panel(A + ke * lda + kb, lda, R - ke, K, ws, stream))) return rc;
-    // (a) update the next panel's columns
-    if ((rc = trailing_update<T>(R - ke, ke2 - ke, K, A + ke * lda + kb, lda, a_bs, A + ke * lda + ke, batch,
-                                 mixed ? ws : nullptr, stream)))
-      return rc;
     const bool more = ke2 < n_pad;
+    const T* P = A + ke * lda + kb;
     if (use_la && more) {
+      // side stream (high priority): (a) the next panel's columns, then that panel's factorisation;
+      // caller's stream: (b) everything to the right of it.  (a) and (b) are independent (both only read panel i), so
+      // they run concurrently and the short (a) no longer costs a kernel tail of its own.
       if ((rc = ce(cudaEventRecord(la.fork, stream)))) return rc;
       if ((rc = ce(cudaStreamWaitEvent(la.side, la.fork, 0)))) return rc;
+      if ((rc = trailing_update<T>(R - ke, ke2 - ke, K, P, lda, a_bs, A + ke * lda + ke, batch, mixed ? ws : nullptr,
+                                   la.side)))
+        return rc;
       if ((rc = factor_panel<T>(A, lda, a_bs, R, ke, ke2, logdet, info, batch, la.side))) return rc;
       if ((rc = ce(cudaEventRecord(la.join, la.side)))) return rc;
-    }
-    // (b) update everything to the right of the next panel
-    if (more) {
       if ((rc = trailing_update<T>(R - ke2, n_pad - ke2, K, A + ke2 * lda + kb, lda, a_bs, A + ke2 * lda + ke2, batch,
                                    mixed ? ws + (ke2 - ke) * K : nullptr, stream)))
         return rc;
-    }
-    if (use_la && more) {
       if ((rc = ce(cudaStreamWaitEvent(stream, la.join, 0)))) return rc;
     } else {
+      if ((rc = trailing_update<T>(R - ke, ke2 - ke, K, P, lda, a_bs, A + ke * lda + ke, batch, mixed ? ws : nullptr,
+                                   stream)))
+        return rc;
+      if (more) {
+        if ((rc = trailing_update<T>(R - ke2, n_pad - ke2, K, A + ke2 * lda + kb, lda, a_bs, A + ke2 * lda + ke2, batch,
+                                     mixed ? ws + (ke2 - ke) * K : nullptr, stream)))
+          return rc;
+      }
       if ((rc = factor_panel<T>(A, lda, a_bs, R, ke, ke2, logdet, info, batch, stream))) return rc;
     }
   }
