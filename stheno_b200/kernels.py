@@ -302,7 +302,15 @@ class Matern52(_Elementary):
 
 
 class Linear(_Elementary):
+    """``<x, y>``.  ``Linear()(x)`` stays a :class:`matrix.LowRank` (``x x^T``), so ``GP(Linear())(x, noise)`` is a
+    Woodbury matrix and ``logpdf`` costs ``O(n d^2)``."""
+
     kind = "linear"
+
+    def _matrix(self, x, y, same):
+        if same:
+            return M.LowRank(x.t, x.origin)
+        return M.Dense(self._pairwise_dev(x, y, same), x.origin)
 
 
 class Delta(_Elementary):
@@ -368,6 +376,8 @@ class ScaledKernel(Kernel):
         if self.flat_terms() is None:
             return M.Dense(self._pairwise_dev(x, y, same), x.origin)
         inner = self.k
+        if same and isinstance(inner, Linear) and float(self.scale) > 0:
+            return M.LowRank(x.t * float(self.scale) ** 0.5, x.origin)
         if same and isinstance(inner, Delta):
             v = float(self.scale)
             return M.fill_diag(v, x.n, x.t.dtype, x.t.device, x.origin) if not x.batch_shape else M.Diagonal(
@@ -594,7 +604,7 @@ class PosteriorKernel(Kernel):
     symmetric = False
 
     def __init__(self, k_ij, k_zi, k_zj, z, K_z):
-        self.k_ij, self.k_zi, self.k_zj, self.z, self.K_z = k_ij, k_zi, k_zj, z, M.as_matrix(K_z)
+        self.k_ij, self.k_zi, self.k_zj, self.z, self.K_z = k_ij, k_zi, k_zj, z, M._densify(K_z)
 
     def _half(self, k_z, x):
         ch = self.K_z.chol()
@@ -647,7 +657,7 @@ class SubspaceKernel(Kernel):
     symmetric = False
 
     def __init__(self, k_zi, k_zj, z, A):
-        self.k_zi, self.k_zj, self.z, self.A = k_zi, k_zj, z, M.as_matrix(A)
+        self.k_zi, self.k_zj, self.z, self.A = k_zi, k_zj, z, M._densify(A)
 
     def _half(self, k_z, x):
         ch = self.A.chol()
@@ -880,7 +890,7 @@ class PosteriorMean(Mean):
     of the factorisation itself."""
 
     def __init__(self, m_i, m_z, k_zi, z, K_z, y, rhs_key=None):
-        self.m_i, self.m_z, self.k_zi, self.z, self.K_z, self.y = m_i, m_z, k_zi, z, M.as_matrix(K_z), y
+        self.m_i, self.m_z, self.k_zi, self.z, self.K_z, self.y = m_i, m_z, k_zi, z, M._densify(K_z), y
         self.rhs_key = rhs_key
         self._b = None
 

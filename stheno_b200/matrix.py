@@ -23,6 +23,8 @@ __all__ = [
     "KernelDense",
     "Diagonal",
     "Zero",
+    "LowRank",
+    "Woodbury",
     "as_matrix",
     "add",
     "dense",
@@ -286,6 +288,94 @@ class Zero(AbstractMatrix):
         return self._describe("zero")
 
 
+class LowRank(AbstractMatrix):
+    """``left @ left^T`` with ``left [..., n, r]`` (what ``Linear()(x)`` is): never materialised unless asked for
+    (SURVEY.md 8f rank 2 -- ``matrix.LowRank`` of the reference's structured-matrix package)."""
+
+    def __init__(self, left, origin=None):
+        self.left = left
+        self.origin = origin
+
+    @property
+    def dev(self):
+        return self.left @ self.left.transpose(-1, -2)
+
+    @property
+    def shape(self):
+        n = self.left.shape[-2]
+        return tuple(self.left.shape[:-2]) + (n, n)
+
+    @property
+    def dtype(self):
+        return self.left.dtype
+
+    @property
+    def device(self):
+        return self.left.device
+
+    @property
+    def T(self):
+        return self
+
+    @property
+    def rank(self):
+        return self.left.shape[-1]
+
+    def __str__(self):
+        return self._describe("low-rank")[:-1] + f", rank={self.rank}>"
+
+
+class Woodbury(AbstractMatrix):
+    """``Diagonal + LowRank``: ``logdet`` and ``iqf`` through the matrix-determinant / matrix-inversion lemmas in
+    ``O(n r^2)`` instead of ``O(n^3)`` (Bayesian linear regression: ``GP(Linear())(x, noise)``)."""
+
+    def __init__(self, diag_m, lr, origin=None):
+        self.diag_m, self.lr = diag_m, lr
+        self.origin = origin
+        self._schur = None
+
+    @property
+    def dev(self):
+        m = self.lr.dev.clone()
+        torch.diagonal(m, dim1=-2, dim2=-1).add_(self.diag_m.diag)
+        return m
+
+    @property
+    def shape(self):
+        return self.lr.shape
+
+    @property
+    def dtype(self):
+        return self.lr.dtype
+
+    @property
+    def device(self):
+        return self.lr.device
+
+    @property
+    def T(self):
+        return self
+
+    def schur(self):
+        """``(I + U^T D^-1 U)`` as a Dense (r x r) with its cached factor; the n r^2 product runs on the tensor-core
+        GEMM (rows of ``U^T D^-1/2`` are K-contiguous)."""
+        if self._schur is None:
+            U, d = self.lr.left, self.diag_m.diag
+            U3, bs = batch_flatten(U, 2)
+            d3 = d.reshape(-1, d.shape[-1]).expand(U3.shape[0], -1)
+            Bn, n, r = U3.shape
+            r_pad, n_pad = ops.round_up(r), ops.round_up(n, 32)
+            Ut = torch.zeros(Bn, r_pad, n_pad, dtype=U.dtype, device=U.device)
+            Ut[:, :r, :n] = (U3 * torch.rsqrt(d3).unsqueeze(-1)).transpose(1, 2)
+            S = ops.gemm_nt(Ut, Ut)[:, :r, :r].clone()
+            S.diagonal(dim1=1, dim2=2).add_(1.0)
+            self._schur = Dense(S.reshape(bs + (r, r)))
+        return self._schur
+
+    def __str__(self):
+        return self._describe("woodbury")[:-1] + f", rank={self.lr.rank}>"
+
+
 # --------------------------------------------------------------------------------------------------------------
 def as_matrix(a, origin=None):
     """``convert(a, AbstractMatrix)`` (``stheno/random.py:110``)."""
@@ -305,6 +395,10 @@ def diag(a):
         return a.diag
     if isinstance(a, Zero):
         return torch.zeros(a.batch_shape + (min(a.rows, a.cols),), dtype=a.dtype, device=a.device)
+    if isinstance(a, LowRank):
+        return (a.left * a.left).sum(-1)
+    if isinstance(a, Woodbury):
+        return a.diag_m.diag + diag(a.lr)
     if isinstance(a, KernelDense) and a._mat is None:
         d = ops.kernel_diag(a.flat, a.xg)
         d = d + a.noise_scalar
@@ -356,6 +450,10 @@ def add(a, b):
         sc = a.scalar + b.scalar if (a.scalar is not None and b.scalar is not None) else None
         return Diagonal(a.diag + b.diag, org, sc)
     if isinstance(b, Diagonal):
+        if isinstance(a, LowRank):
+            return Woodbury(b, a, org)
+        if isinstance(a, Woodbury):
+            return Woodbury(add(a.diag_m, b), a.lr, org)
         if isinstance(a, KernelDense) and a._mat is None and a._chol is None:
             if b.scalar is not None:
                 return a.with_noise(scalar=b.scalar, scalar_t=getattr(b, "scalar_t", None))
@@ -366,18 +464,27 @@ def add(a, b):
     return Dense(a.dev + b.dev, org)
 
 
+def _densify(a):
+    """Structured types without a fast path for the requested operation fall back to their dense form."""
+    if isinstance(a, (LowRank, Woodbury)):
+        return Dense(a.dev, a.origin)
+    return as_matrix(a)
+
+
 def cholesky(a):
     """``B.cholesky``: an :class:`ops.Chol` for Dense, the element-wise root for Diagonal."""
     if isinstance(a, Diagonal):
         return Diagonal(torch.sqrt(a.diag), a.origin)
-    return as_matrix(a).chol()
+    return _densify(a).chol()
 
 
 def logdet(a):
     """``B.logdet`` -> ``[...]`` (``stheno/random.py:274``, ``stheno/model/observations.py:334``)."""
     if isinstance(a, Diagonal):
         return torch.log(a.diag).sum(-1)
-    a = as_matrix(a)
+    if isinstance(a, Woodbury):  # det(D + U U^T) = det(D) det(I + U^T D^-1 U)
+        return torch.log(a.diag_m.diag).sum(-1) + logdet(a.schur())
+    a = _densify(a)
     return a.chol().logdet.reshape(a.shape[:-2])
 
 
@@ -392,7 +499,9 @@ def iqf_diag(a, b, c=None):
     if isinstance(a, Diagonal):
         c = b if c is None else c
         return (b * c / a.diag.unsqueeze(-1)).sum(-2)
-    a = as_matrix(a)
+    if isinstance(a, Woodbury):
+        return torch.diagonal(iqf(a, b, c), dim1=-2, dim2=-1)
+    a = _densify(a)
     ch = a.chol()
     bt, bs = _rows(b)
     hb = ch.half_solve(bt.contiguous())
@@ -405,7 +514,15 @@ def iqf(a, b, c=None):
     if isinstance(a, Diagonal):
         c = b if c is None else c
         return b.transpose(-1, -2) @ (c / a.diag.unsqueeze(-1))
-    a = as_matrix(a)
+    if isinstance(a, Woodbury):
+        # (D + U U^T)^-1 = D^-1 - D^-1 U (I + U^T D^-1 U)^-1 U^T D^-1
+        c = b if c is None else c
+        dinv = 1.0 / a.diag_m.diag.unsqueeze(-1)
+        U = a.lr.left
+        ub = U.transpose(-1, -2) @ (b * dinv)  # [..., r, kb]
+        uc = ub if c is b else U.transpose(-1, -2) @ (c * dinv)
+        return b.transpose(-1, -2) @ (c * dinv) - iqf(a.schur(), ub, uc)
+    a = _densify(a)
     ch = a.chol()
     bt, bs = _rows(b)
     hb = ch.half_solve(bt.contiguous())
@@ -456,5 +573,9 @@ def submatrix(a, mask):
         return Zero(a.dtype, n, n, a.device, a.batch_shape, a.origin)
     if isinstance(a, Diagonal):
         return Diagonal(a.diag[..., mask], a.origin, a.scalar)
+    if isinstance(a, LowRank):
+        return LowRank(a.left[..., mask, :], a.origin)
+    if isinstance(a, Woodbury):
+        return Woodbury(submatrix(a.diag_m, mask), submatrix(a.lr, mask), a.origin)
     m = dense(a)
     return Dense(m[..., mask, :][..., :, mask], getattr(a, "origin", None))

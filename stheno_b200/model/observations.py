@@ -71,6 +71,7 @@ class Observations(AbstractObservations):
             return self._K_x[id(measure)]
         except KeyError:
             K_x = M.add(pairwise(measure.kernels[self.fdd.p], self.fdd.x), self.fdd.noise)
+            K_x = M._densify(K_x)  # low-rank structure is exploited by logpdf; conditioning uses the dense factor
             if isinstance(K_x, M.Dense):
                 diff = self.y - measure.means[self.fdd.p].dev(self.fdd.x)
                 d3, _ = batch_flatten(diff, 2)
@@ -171,7 +172,7 @@ class AbstractPseudoObservations(AbstractObservations):
             raise RuntimeError(
                 f'Kernel matrix of observation noise must be diagonal, not "{type(K_n).__name__}".'
             )
-        K_z = M.as_matrix(K_z)
+        K_z = M._densify(K_z)
         ch_z = K_z.chol()  # :300
         m, m_pad = ch_z.n, ch_z.n_pad
         # :285 + :301  W^T = (L_z^-1 K_zx)^T, rows = data points, zero padded [B, n_pad, m_pad]

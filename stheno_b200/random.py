@@ -201,11 +201,13 @@ class Normal(RandomVector):
                 return sub.logpdf(from_dev(xd[avail], out_origin))
         n = var.shape[-1]
         diff = xd if self.mean_is_zero else xd - self._mean_dev()
-        if isinstance(var, M.Diagonal):
+        if isinstance(var, (M.Diagonal, M.Woodbury)):
             ld = M.logdet(var)
             q = M.iqf_diag(var, diff)
             lp = -(ld.unsqueeze(-1) + n * B.log_2_pi + q) / 2
         else:
+            if isinstance(var, M.LowRank):
+                var = M.Dense(var.dev, var.origin)
             d3, bs = batch_flatten(diff, 2)
             rhs_t = d3.transpose(1, 2).contiguous()  # [B, k, n]: right-hand sides as rows
             if isinstance(var, M.KernelDense) and (var.needs_grad() or (torch.is_grad_enabled() and rhs_t.requires_grad)):
@@ -260,7 +262,7 @@ class Normal(RandomVector):
         elif isinstance(var, M.Zero):
             s = torch.zeros(bs + (n, num), dtype=var.dtype, device=var.device)
         else:
-            ch = var.chol()
+            ch = M.cholesky(var)
             eps = torch.randn((ch.batch, n, num), dtype=var.dtype, device=var.device, generator=state)
             s = (ch.L() @ eps).reshape(bs + (n, num))
         if not self.mean_is_zero:

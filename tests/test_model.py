@@ -501,3 +501,28 @@ def test_normal_arithmetic_and_lazy_contracts(S):
     lm = S.Normal(np.ones((2, 1)), np.eye(2)).lmatmul(a)
     approx(S.B.dense(lm.var), a @ a.T)
     approx(lm.mean, a @ np.ones((2, 1)))
+
+
+def test_linear_kernel_stays_low_rank(S):
+    # Linear() + diagonal noise -> Woodbury: logpdf / posterior in O(n d^2), same numbers as dense
+    rng = np.random.default_rng(40)
+    n, d = 200, 3
+    x = rng.standard_normal((n, d))
+    y = rng.standard_normal(n)
+    f = S.GP(2.0 * S.Linear())
+    fd = f(x, 0.3)
+    assert isinstance(fd.var, S.matrix.Woodbury) and isinstance(f(x).var, S.matrix.LowRank)
+    spec = ("scaled", 2.0, ("linear",))
+    approx(fd.logpdf(y), O.fdd_logpdf(spec, x, 0.3, y), rtol=1e-9)
+    approx(S.B.dense(fd.var), O.kernel_matrix(spec, x) + 0.3 * np.eye(n), rtol=1e-12, atol=1e-12)
+    approx(fd.var_diag, np.diag(O.kernel_matrix(spec, x)) + 0.3, rtol=1e-12)
+    noise_vec = rng.uniform(0.2, 0.5, n)
+    approx(f(x, noise_vec).logpdf(y), O.fdd_logpdf(spec, x, noise_vec, y), rtol=1e-9)
+    xs = rng.standard_normal((7, d))
+    post = f | (f(x, 0.3), y)
+    mref, vref = O.posterior(spec, x, 0.3, y, xs)
+    approx(post(xs).mean, mref, rtol=1e-7, atol=1e-8)
+    approx(S.B.dense(post(xs).var), vref, rtol=1e-6, atol=1e-8)
+    # a sum with a dense kernel falls back to the dense path and still agrees
+    g = S.GP(S.Linear() + S.EQ())
+    approx(g(x, 0.3).logpdf(y), O.fdd_logpdf(("sum", ("linear",), ("eq",)), x, 0.3, y), rtol=1e-9)
