@@ -2,7 +2,7 @@
 // accuracy through the 3xTF32 split:   a = a_hi + a_lo  (a_hi = the 19 bits the TF32 datapath keeps, a_lo = a - a_hi)
 //     a b  ~=  a_hi b_hi + a_hi b_lo + a_lo b_hi        (relative error ~2^-21, the fp32 FFMA kernel's is 2^-24)
 //
-// One 128 x 128 output tile per CTA, fp32 accumulator in TMEM (128 lanes x 128 columns), 6 warps:
+// One 128 x 128 or 128 x 256 output tile per CTA, fp32 accumulator in TMEM (128 lanes x 128 / 256 columns), 6 warps:
 //   warp 0      TMA producer: 128 x 32 fp32 tiles of A and B per k-block (cp.async.bulk.tensor.3d, SWIZZLE_128B,
 //               mbarrier complete_tx) into a 3-stage ring
 //   warps 2-5   splitter: as soon as a stage lands they write the low parts a - trunc_tf32(a) of both tiles next to it
@@ -22,11 +22,18 @@
 
 namespace gpk {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
-constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;         // 16 KB
-constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;        // A, A_lo, B, B_lo
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024;
+constexpr int TC_BM = 128, TC_BK = 32;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB per A tile
 constexpr int TC_GEMM_THREADS = 192;
+// BN = 128: stage = A, A_lo, B, B_lo = 64 KB, 3 stages.  BN = 256: stage = 16 + 16 + 32 + 32 = 96 KB, 2 stages -- the
+// same bytes in flight, but every staged byte feeds twice the MMA work (the kernel is bound by bytes-in-flight / latency).
+template <int BN>
+struct TcCfg {
+  static constexpr int B_BYTES = BN * TC_BK * 4;
+  static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (BN == 128) ? 3 : 2;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+};
 
 struct TcParams {
   float alpha, beta;
@@ -89,10 +96,13 @@ __device__ __forceinline__ float4 tf32_low_part(float4 v) {
 
 // CT = type of C: float (fp32 problems) or double (opt-in mixed precision: fp64 matrix, fp32 operands -- the
 // "tf32 where the user opts in" trailing update of the fp64 Cholesky).
-template <typename CT>
+template <typename CT, int TC_BN>
 __global__ void __launch_bounds__(TC_GEMM_THREADS, 1)
 gemm_nt_f32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                       const TcParams p) {
+  using Cfg = TcCfg<TC_BN>;
+  constexpr int TC_STAGES = Cfg::STAGES, TC_STAGE_BYTES = Cfg::STAGE_BYTES, TC_TILE_BYTES = TC_A_BYTES;
+  constexpr int TC_B_BYTES = Cfg::B_BYTES;
   int tm, tn;
   {
     const int GROUP = 8, per_group = GROUP * p.tiles_n, id = blockIdx.x;
@@ -101,7 +111,7 @@ gemm_nt_f32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     tm = first_m + r % gsize;
     tn = r / gsize;
   }
-  if (p.lower && tn > tm) return;
+  if (p.lower && tn * TC_BN >= (tm + 1) * TC_BM) return;
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -112,7 +122,7 @@ gemm_nt_f32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_holder)),
-                 "r"(128));
+                 "r"(TC_BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
   }
   if (threadIdx.x == 32) {
@@ -136,7 +146,7 @@ gemm_nt_f32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         const int s = kb % TC_STAGES, it = kb / TC_STAGES;
         if (it > 0) mbar_wait_parity(&empty_bar[s], (it - 1) & 1);
         uint8_t* st = smem + s * TC_STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], 2 * TC_TILE_BYTES);
+        mbar_arrive_expect_tx(&full_bar[s], TC_TILE_BYTES + TC_B_BYTES);
         tma_load_3d(st, &mapA, kb * TC_BK, tm * TC_BM, b, &full_bar[s]);
         tma_load_3d(st + 2 * TC_TILE_BYTES, &mapB, kb * TC_BK, tn * TC_BN, b, &full_bar[s]);
       }
@@ -151,7 +161,7 @@ gemm_nt_f32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         mbar_wait_parity(&split_bar[s], it & 1);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
         const uint32_t a_hi = smem_u32(smem + s * TC_STAGE_BYTES), a_lo = a_hi + TC_TILE_BYTES;
-        const uint32_t b_hi = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
+        const uint32_t b_hi = a_hi + 2 * TC_TILE_BYTES, b_lo = b_hi + TC_B_BYTES;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {  // UMMA K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
           const uint32_t off = ks * 32;
@@ -172,12 +182,11 @@ gemm_nt_f32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       float4* hiA = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES);
       float4* loA = hiA + TC_TILE_BYTES / 16;
       float4* hiB = hiA + 2 * TC_TILE_BYTES / 16;
-      float4* loB = hiA + 3 * TC_TILE_BYTES / 16;
+      float4* loB = hiB + TC_B_BYTES / 16;
 #pragma unroll 4
-      for (int i = t; i < TC_TILE_BYTES / 16; i += 128) {
-        loA[i] = tf32_low_part(hiA[i]);
-        loB[i] = tf32_low_part(hiB[i]);
-      }
+      for (int i = t; i < TC_TILE_BYTES / 16; i += 128) loA[i] = tf32_low_part(hiA[i]);
+#pragma unroll 4
+      for (int i = t; i < TC_B_BYTES / 16; i += 128) loB[i] = tf32_low_part(hiB[i]);
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
       mbar_arrive(&split_bar[s]);
     }
@@ -189,7 +198,7 @@ gemm_nt_f32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     CT* Crow = static_cast<CT*>(p.C) + (int64_t)b * p.c_bs + ((int64_t)tm * TC_BM + row) * p.ldc + (int64_t)tn * TC_BN;
     const float alpha = p.alpha, beta = p.beta;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < TC_BN / 32; ++c) {
       uint32_t r[32];
       const uint32_t taddr = tmem + ((uint32_t)(lane_group * 32) << 16) + c * 32;
       asm volatile(
@@ -239,7 +248,7 @@ gemm_nt_f32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(128));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(TC_BN));
 }
 
 // ---- host ------------------------------------------------------------------------------------------------------------
@@ -257,38 +266,51 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-static bool make_map(CUtensorMap* m, const float* base, int64_t K, int64_t rows, int64_t ld, int64_t bs, int32_t batch) {
+static bool make_map(CUtensorMap* m, const float* base, int64_t K, int64_t rows, int64_t ld, int64_t bs, int32_t batch,
+                     int box_rows) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return false;
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)((batch > 1) ? bs : rows * ld) * 4};
-  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM, 1};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows, 1};
   cuuint32_t es[3] = {1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename CT>
-static int launch_tc(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, int64_t a_bs,
-                     const float* B, int64_t ldb, int64_t b_bs, float beta, CT* C, int64_t ldc, int64_t c_bs, int32_t lower,
-                     int32_t batch, cudaStream_t stream) {
+template <typename CT, int BN>
+static int launch_tc_bn(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, int64_t a_bs,
+                        const float* B, int64_t ldb, int64_t b_bs, float beta, CT* C, int64_t ldc, int64_t c_bs,
+                        int32_t lower, int32_t batch, cudaStream_t stream) {
   CUtensorMap mA, mB;
-  if (!make_map(&mA, A, K, M, lda, a_bs, batch) || !make_map(&mB, B, K, N, ldb, b_bs, batch)) return 0;
+  if (!make_map(&mA, A, K, M, lda, a_bs, batch, TC_BM) || !make_map(&mB, B, K, N, ldb, b_bs, batch, BN)) return 0;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(gemm_nt_f32_tc_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_nt_f32_tc_kernel<CT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TcCfg<BN>::SMEM_BYTES);
     if (e != cudaSuccess) return -1000 - (int)e;
     attr_set = true;
   }
-  TcParams p{alpha, beta, C, ldc, c_bs, (int32_t)K, lower, (int32_t)(M / TC_BM), (int32_t)(N / TC_BN)};
+  TcParams p{alpha, beta, C, ldc, c_bs, (int32_t)K, lower, (int32_t)(M / TC_BM), (int32_t)(N / BN)};
   dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch);
-  gemm_nt_f32_tc_kernel<CT><<<grid, TC_GEMM_THREADS, TC_SMEM_BYTES, stream>>>(mA, mB, p);
+  gemm_nt_f32_tc_kernel<CT, BN><<<grid, TC_GEMM_THREADS, TcCfg<BN>::SMEM_BYTES, stream>>>(mA, mB, p);
   GPK_COUNT_LAUNCH();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return -1000 - (int)e;
   return 1;
+}
+
+template <typename CT>
+static int launch_tc(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, int64_t a_bs,
+                     const float* B, int64_t ldb, int64_t b_bs, float beta, CT* C, int64_t ldc, int64_t c_bs, int32_t lower,
+                     int32_t batch, cudaStream_t stream) {
+  // 128 x 256 tiles when there are enough of them to fill the machine (each staged byte feeds twice the MMA work)
+  static const int force_bn = getenv("GPK_TC_BN") ? atoi(getenv("GPK_TC_BN")) : 0;
+  const bool wide = (force_bn == 256) || (force_bn == 0 && N % 256 == 0 && (M / TC_BM) * (N / 256) * batch >= 148);
+  if (wide && N % 256 == 0)
+    return launch_tc_bn<CT, 256>(M, N, K, alpha, A, lda, a_bs, B, ldb, b_bs, beta, C, ldc, c_bs, lower, batch, stream);
+  return launch_tc_bn<CT, 128>(M, N, K, alpha, A, lda, a_bs, B, ldb, b_bs, beta, C, ldc, c_bs, lower, batch, stream);
 }
 
 // returns 1 if the problem was launched on the tcgen05 path, 0 if the caller should use the FFMA kernel, < 0 on error
@@ -296,7 +318,7 @@ int gemm_nt_f32_tc(int64_t M, int64_t N, int64_t K, float alpha, const float* A,
                    int64_t ldb, int64_t b_bs, float beta, float* C, int64_t ldc, int64_t c_bs, int32_t lower,
                    int32_t batch, cudaStream_t stream) {
   static const bool disabled = getenv("GPK_F32_FFMA") != nullptr;
-  if (disabled || K < 128 || K % TC_BK || M % TC_BM || N % TC_BN) return 0;
+  if (disabled || K < 128 || K % TC_BK || M % TC_BM || N % 128) return 0;
   if (lda % 4 || ldb % 4 || ldc % 4 || (batch > 1 && (a_bs % 4 || b_bs % 4))) return 0;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) % 16) return 0;
   return launch_tc<float>(M, N, K, alpha, A, lda, a_bs, B, ldb, b_bs, beta, C, ldc, c_bs, lower, batch, stream);
@@ -314,7 +336,7 @@ __global__ void f64_to_f32_panel_kernel(const double* __restrict__ src, int64_t 
 
 // C[M x N] (lower tiles) -= P[0:M] P[0:N]^T, P = fp64 panel (M x K, ld = ldp) converted into ws (M x K floats).
 int syrk_f64_tf32x3(int64_t M, int64_t N, int64_t K, const float* ws_rows, double* C, int64_t ldc, cudaStream_t stream) {
-  if (K % TC_BK || M % TC_BM || N % TC_BN || K < 128) return GPK_ERR_ARG;
+  if (K % TC_BK || M % TC_BM || N % 128 || K < 128) return GPK_ERR_ARG;
   const int rc = launch_tc<double>(M, N, K, -1.0f, ws_rows, K, 0, ws_rows, K, 0, 1.0f, C, ldc, 0, 1, 1, stream);
   return rc == 1 ? 0 : (rc < 0 ? rc : GPK_ERR_UNSUPPORTED);
 }
