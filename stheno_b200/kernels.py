@@ -31,12 +31,13 @@ __all__ = [
 class Input:
     """A numeric input on the device, ``[..., n, d]`` (vectors are up-ranked to columns like ``B.uprank``)."""
 
-    __slots__ = ("t", "origin", "_groups")
+    __slots__ = ("t", "origin", "_groups", "src")
 
     def __init__(self, x):
         self.origin = origin_of(x)
         self.t = uprank(to_dev(x))
         self._groups = {}
+        self.src = x  # the caller's object: "x is y" semantics of the reference survive the move to the device
 
     @property
     def n(self):
@@ -568,6 +569,8 @@ def pairwise(k, x, y=None):
         return mo_pairwise(k, x, x if same else y, same)
     xi = as_input(x)
     yi = xi if same else as_input(y)
+    if not same and getattr(xi, "src", None) is not None and getattr(yi, "src", None) is xi.src:
+        same, yi = True, xi  # two wrappers of the caller's same array (e.g. f1(x), f2(x)): the same points
     return k._matrix(xi, yi, same)
 
 

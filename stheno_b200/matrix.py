@@ -163,8 +163,20 @@ class KernelDense(Dense):
     @property
     def dev(self):
         if self._mat is None:
-            K = ops.kernel_matrix(self.flat, self.xg.detach(), noise_scalar=self.noise_scalar,
-                                  noise_vec=None if self.noise_vec is None else self.noise_vec.detach())
+            if self.needs_grad():
+                # differentiable materialisation (covariances assembled from several kernel matrices, e.g. multi-output
+                # joints): K1 forward + K1-backward through torch autograd; the diagonal noise is added with torch ops
+                from .autograd import kernel_matrix_grad
+
+                K = kernel_matrix_grad(self.flat, self.xg)
+                nz = self.noise_t if self.noise_t is not None else self.noise_scalar
+                eye = torch.eye(self.n, dtype=K.dtype, device=K.device)
+                K = K + nz * eye
+                if self.noise_vec is not None:
+                    K = K + torch.diag_embed(self.noise_vec)
+            else:
+                K = ops.kernel_matrix(self.flat, self.xg.detach(), noise_scalar=self.noise_scalar,
+                                      noise_vec=None if self.noise_vec is None else self.noise_vec.detach())
             self._mat = K.reshape(self.batch_shape + (self.n, self.n))
         return self._mat
 

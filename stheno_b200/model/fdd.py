@@ -29,7 +29,7 @@ def _noise_as_matrix(noise, dtype, device, n, origin, batch_shape=()):
     if isinstance(noise, (int, float, np.number)) or (isinstance(noise, (np.ndarray, torch.Tensor)) and noise.ndim == 0):
         if isinstance(noise, torch.Tensor) and noise.requires_grad:
             shape = tuple(batch_shape) + (n,)
-            return M.Diagonal(noise.to(device=device, dtype=dtype).expand(shape), origin, scalar=float(noise),
+            return M.Diagonal(noise.to(device=device, dtype=dtype).expand(shape), origin, scalar=float(noise.detach()),
                               scalar_t=noise)
         if batch_shape:
             v = float(noise)

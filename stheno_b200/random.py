@@ -212,6 +212,12 @@ class Normal(RandomVector):
             rhs_t = d3.transpose(1, 2).contiguous()  # [B, k, n]: right-hand sides as rows
             if isinstance(var, M.KernelDense) and (var.needs_grad() or (torch.is_grad_enabled() and rhs_t.requires_grad)):
                 lp = var.logpdf_grad(rhs_t)  # analytic backward (autograd.py)
+            elif (not isinstance(var, M.KernelDense) and torch.is_grad_enabled()
+                  and (var.dev.requires_grad or rhs_t.requires_grad)):
+                from .autograd import dense_logpdf
+
+                K3, _ = batch_flatten(var.dev, 2)
+                lp = dense_logpdf(K3, rhs_t, B.epsilon)  # gradient w.r.t. the assembled covariance itself
             elif var._chol is None:
                 key = ("logpdf", id(xd))
                 var.attach_rhs(key, rhs_t)

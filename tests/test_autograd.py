@@ -77,3 +77,45 @@ def test_optimisation_loop_decreases_loss():
         opt.step()
         losses.append(loss.item())
     assert losses[-1] < losses[0] - 10
+
+
+def test_multi_output_joint_gradients():
+    """BASELINE config 5 in miniature: p = 3 outputs mixing m = 2 latent GPs (ILMM, readme_example4_multi-output.py),
+    loss = -joint logpdf, gradients w.r.t. the mixing matrix H, the latent length scales and the noise -- through the block
+    assembly of stheno/mo -- against torch autograd on a plain dense restatement."""
+    import stheno_b200 as S
+
+    S.B.epsilon = 1e-12
+    torch.manual_seed(0)
+    n, p, m = 60, 3, 2
+    x = torch.linspace(0, 5, n, dtype=torch.float64, device="cuda")
+    y = torch.randn(p * n, dtype=torch.float64, device="cuda")
+
+    def params():
+        H = torch.tensor([[1.0, 0.5], [-0.7, 1.2], [0.3, -0.9]], dtype=torch.float64, device="cuda", requires_grad=True)
+        ells = torch.tensor([0.8, 1.9], dtype=torch.float64, device="cuda", requires_grad=True)
+        noise = torch.tensor(0.3, dtype=torch.float64, device="cuda", requires_grad=True)
+        return H, ells, noise
+
+    H, ells, noise = params()
+    meas = S.Measure()
+    us = [S.GP(S.EQ().stretch(ells[j]), measure=meas) for j in range(m)]
+    fs = [H[i, 0] * us[0] + H[i, 1] * us[1] for i in range(p)]
+    lp = meas.logpdf(*[(fs[i](x, noise), y[i * n:(i + 1) * n]) for i in range(p)])
+    assert lp.requires_grad
+    (-lp).backward()
+    got = [H.grad.clone(), ells.grad.clone(), noise.grad.clone()]
+
+    H, ells, noise = params()
+    d2 = (x[:, None] - x[None, :]) ** 2
+    Ks = [torch.exp(-0.5 * d2 / ells[j] ** 2) for j in range(m)]
+    K = torch.cat([torch.cat([sum(H[i, j] * H[k, j] * Ks[j] for j in range(m)) for k in range(p)], dim=1) for i in range(p)], dim=0)
+    K = K + (noise + 1e-12) * torch.eye(p * n, dtype=torch.float64, device="cuda")
+    L = torch.linalg.cholesky(K)
+    a = torch.linalg.solve_triangular(L, y[:, None], upper=False)
+    ref = -0.5 * (2 * torch.log(torch.diagonal(L)).sum() + p * n * np.log(2 * np.pi) + (a * a).sum())
+    (-ref).backward()
+    assert abs(lp.item() - ref.item()) < 1e-10 * abs(ref.item())
+    for a_, b_, name in zip(got, [H.grad, ells.grad, noise.grad], ["H", "ells", "noise"]):
+        err = (a_ - b_).abs().max().item()
+        assert err < 1e-7 * max(1.0, b_.abs().max().item()), (name, err, a_, b_)
