@@ -207,7 +207,7 @@ class Kernel:
                     keys[k] = len(scales)
                     scales.append(s)
                 nf.append((kind, keys[k]))
-            out.append((float(coef), nf))
+            out.append((float(coef.detach()) if isinstance(coef, torch.Tensor) else float(coef), nf))
             raw.append(coef)
         if not scales:
             scales = [None]
