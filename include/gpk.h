@@ -141,6 +141,21 @@ int gpk_potrf_f32(float* A, int64_t lda, int64_t a_bstride, int64_t n_pad, int64
 int gpk_potrf_f64_tf32x3(double* A, int64_t lda, int64_t a_bstride, int64_t n_pad, int64_t extra_rows, double* logdet,
                          int32_t* info, int32_t batch, float* ws, int64_t ws_elems, void* stream);
 
+/* fp64 emulation on the INT8 tensor cores (tcgen05.mma.kind::i8; Ozaki splitting): every row of the panel is scaled by
+ * a power of two and split error-free into `slices` signed 7-bit integers; the slice products are EXACT in int32 and are
+ * recombined in fp64.  6 slices: 21 int8 GEMMs, product error ~2^-40 |a||b| (zero-mean); 7 slices: 28 GEMMs, ~2^-47.
+ * `ws`: 1024-byte aligned workspace of gpk_potrf_oz_ws_bytes(n_pad, extra_rows, slices) bytes.  Same contract as
+ * gpk_potrf_f64 otherwise (batch must be 1 for the emulated update; batched problems fall back to the DMMA update). */
+int64_t gpk_potrf_oz_ws_bytes(int64_t n_pad, int64_t extra_rows, int32_t slices);
+int gpk_potrf_f64_oz(double* A, int64_t lda, int64_t a_bstride, int64_t n_pad, int64_t extra_rows, double* logdet,
+                     int32_t* info, int32_t batch, int32_t slices, void* ws, int64_t ws_bytes, void* stream);
+/* The emulated GEMM on its own: C = beta C + alpha A B^T (M % 128 == 0, N % 64 == 0, K % 128 == 0, K <= 65536).
+ * `ws`: 1024-byte aligned, >= round_up(gpk_oz_ws_bytes(M, K, slices), 1024) + gpk_oz_ws_bytes(N, K, slices) bytes. */
+int64_t gpk_oz_ws_bytes(int64_t rows, int64_t K, int32_t slices);
+int gpk_gemm_nt_f64_oz(int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, const double* B,
+                       int64_t ldb, double beta, double* C, int64_t ldc, int32_t lower, int32_t slices, void* ws,
+                       int64_t ws_bytes, void* stream);
+
 /* K3: X * L^T = B  in place (B: rows x n_pad, rows a multiple of 64; L: n_pad x n_pad lower).
  * Row r of the result is (L^-1 b_r)^T.  Replaces B.solve(L, .) / B.iqf:  stheno/model/observations.py:301 and
  * the PosteriorMean / PosteriorKernel evaluation behind observations.py:143-168. */

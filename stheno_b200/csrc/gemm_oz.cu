@@ -1,0 +1,412 @@
+// fp64 GEMM  C = beta*C + alpha * A * B^T  emulated on the 5th-generation tensor cores' INT8 path
+// (tcgen05.mma.kind::i8, int32 accumulators in TMEM) with the Ozaki splitting: every row of A and B is scaled by a power
+// of two (its largest magnitude) and cut into S signed 7-bit slices
+//        a = 2^e * sum_s  q_s 2^-(6+7s),   q_s = round-to-nearest of the running remainder, |q_s| <= 64   (error-free)
+// so that   a . b = 2^(e_a+e_b) * sum_{s,t} 2^-(12+7(s+t)) * (q_s . r_t),   and every integer dot product q_s . r_t is
+// EXACT in int32 (|q r| <= 2^12, K <= 65536, up to S products per accumulator).  Products with s + t >= S are dropped
+// (they are below the slicing error), leaving S(S+1)/2 int8 GEMMs -- 21 for S = 6 (error ~2^-40 of |a||b|, zero-mean), 28
+// for S = 7 (~2^-47) -- against the 8192 MAC/clk/SM of the int8 pipe instead of the 64 FMA/clk/SM of DMMA.
+//
+// One 128 x 64 output tile per CTA; products with the same s + t share an accumulator: S accumulators x 64 TMEM columns.
+//   warp 0      TMA producer: per 64-byte k-block ONE box {64 B, 128 rows, S slices} of A and one {64 B, 64 rows, S} of B
+//               (cp.async.bulk.tensor.3d, SWIZZLE_64B, mbarrier complete_tx) into a 3- (S <= 6) or 2-stage ring
+//   warp 1      MMA issuer: S(S+1)/2 x 2 tcgen05.mma.kind::i8 (M=128, N=64, K=32) per k-block, tcgen05.commit per stage
+//   warps 2-5   epilogue: tcgen05.ld the S accumulators 16 columns at a time, Horner-combine them in fp64 (exact int32 ->
+//               double through the 2^52 trick), scale by 2^(e_row + e_col), C read-modify-write
+// The slicing kernel (oz_slice_kernel) is O(rows*K) and runs once per panel; in the Cholesky its output is shared by
+// every tile of the trailing update.
+//
+// SASS evidence: UTCIMMA / UTCHMMA (tcgen05.mma), UTMALDG (TMA), LDTM (tcgen05.ld), UTCBAR (tcgen05.commit).
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace gpk {
+namespace {
+
+constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 64;  // BK in bytes = int8 elements
+constexpr int OZ_THREADS = 192;
+
+template <int S>
+struct OzCfg {
+  static constexpr int A_SLICE = OZ_BM * OZ_BK;  // 8 KB
+  static constexpr int B_SLICE = OZ_BN * OZ_BK;  // 4 KB
+  static constexpr int A_BYTES = S * A_SLICE;
+  static constexpr int B_BYTES = S * B_SLICE;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (3 * STAGE_BYTES + 1024 <= 227 * 1024) ? 3 : 2;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+  static constexpr int TMEM_COLS = 512;  // S * 64 rounded up to a power of two (S = 5..8)
+};
+
+struct OzParams {
+  double alpha, beta;
+  double* C;
+  const double* sc_a;  // 2^e per A row (already offset to the first row of the problem)
+  const double* sc_b;
+  int64_t ldc;
+  int32_t a_row0, b_row0;  // first plane row of A / B
+  int32_t KB, lower, tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ void oz_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "OZW_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra OZW_DONE;\n"
+      "bra OZW_LOOP;\n"
+      "OZW_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity));
+}
+__device__ __forceinline__ void oz_tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+// K-major SWIZZLE_64B shared-memory matrix descriptor: start address >> 4, LBO = 1 (ignored for swizzled K-major),
+// SBO = 512 B (8 rows x 64 B) >> 4 = 32, version 1 (Blackwell), layout type 4 (SWIZZLE_64B).
+__device__ __forceinline__ uint64_t oz_desc(uint32_t smem_addr) {
+  const uint64_t hi = (uint64_t)(32u | (1u << 14) | (4u << 29)) << 32;
+  return hi | (uint64_t)(((smem_addr >> 4) & 0x3FFFu) | (1u << 16));
+}
+__device__ __forceinline__ void oz_umma_i8(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n"
+      "}\n" ::"r"(tmem_c),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0));
+}
+__device__ __forceinline__ void oz_umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void oz_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// exact int32 -> double without the conversion pipe: bits(2^52 + 2^31 + x) = 0x43300000 : (x ^ 0x80000000)
+__device__ __forceinline__ double oz_i2d(uint32_t x) {
+  return __hiloint2double(0x43300000, (int)(x ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
+}
+
+template <int S>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const OzParams p) {
+  using Cfg = OzCfg<S>;
+  constexpr int STAGES = Cfg::STAGES;
+  int tm, tn;
+  {
+    const int GROUP = 8, per_group = GROUP * p.tiles_n, id = blockIdx.x;
+    const int group = id / per_group, first_m = group * GROUP, gsize = min(p.tiles_m - first_m, GROUP);
+    const int r = id - group * per_group;
+    tm = first_m + r % gsize;
+    tn = r / gsize;
+  }
+  if (p.lower && tn * OZ_BN >= (tm + 1) * OZ_BM) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  extern __shared__ uint8_t oz_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_holder;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_holder)),
+                 "r"(Cfg::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  }
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    fence_mbar_init();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+  const uint32_t tmem = tmem_base_holder;
+  const int KB = p.KB;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES, it = kb / STAGES;
+        if (it > 0) oz_mbar_wait(&empty_bar[s], (it - 1) & 1);
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        oz_tma_load_3d(st, &mapA, kb * OZ_BK, p.a_row0 + tm * OZ_BM, 0, &full_bar[s]);
+        oz_tma_load_3d(st + Cfg::A_BYTES, &mapB, kb * OZ_BK, p.b_row0 + tn * OZ_BN, 0, &full_bar[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), K-major, N >> 3 at 17, M >> 4 at 24
+      const uint32_t idesc =
+          (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES, it = kb / STAGES;
+        oz_mbar_wait(&full_bar[s], it & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+        const uint32_t a0 = smem_u32(smem + s * Cfg::STAGE_BYTES), b0 = a0 + Cfg::A_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {  // UMMA K = 32 int8 = 32 bytes inside the 64-byte swizzle row
+#pragma unroll
+          for (int sa = 0; sa < S; ++sa) {
+#pragma unroll
+            for (int sb = 0; sb + sa < S; ++sb) {
+              oz_umma_i8(tmem + (uint32_t)((sa + sb) * OZ_BN), oz_desc(a0 + sa * Cfg::A_SLICE + ks * 32),
+                         oz_desc(b0 + sb * Cfg::B_SLICE + ks * 32), idesc, (kb > 0 || ks > 0 || sa > 0) ? 1u : 0u);
+            }
+          }
+        }
+        oz_umma_commit(&empty_bar[s]);
+      }
+      oz_umma_commit(&accum_bar);
+    }
+  } else {
+    // ---- epilogue: TMEM -> registers -> fp64 combine -> C (read-modify-write) ----
+    const int lane_group = warp & 3;  // a warp may only touch TMEM lanes 32 * (warp % 4) .. + 31
+    const int row = lane_group * 32 + lane;
+    // 2^-(12 + 7 (S-1)): weight of the last kept diagonal; Horner runs from diagonal 0 (largest weight) down
+    const double w_last = __hiloint2double((1023 - (12 + 7 * (S - 1))) << 20, 0);
+    const double rs = p.alpha * w_last * __ldg(p.sc_a + (int64_t)tm * OZ_BM + row);
+    const double* cs = p.sc_b + (int64_t)tn * OZ_BN;
+    double* Crow = p.C + ((int64_t)tm * OZ_BM + row) * p.ldc + (int64_t)tn * OZ_BN;
+    const double beta = p.beta;
+    oz_mbar_wait(&accum_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+#pragma unroll 1
+    for (int c = 0; c < OZ_BN / 16; ++c) {
+      double2 o[8];
+      double2* cp = reinterpret_cast<double2*>(Crow + c * 16);
+      if (beta != 0.0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = cp[j];
+      }
+      double v[16];
+      const uint32_t taddr = tmem + ((uint32_t)(lane_group * 32) << 16) + c * 16;
+      {
+        uint32_t r[16];
+        oz_tmem_ld16(taddr, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = oz_i2d(r[j]);
+      }
+#pragma unroll
+      for (int d = 1; d < S; ++d) {
+        uint32_t r[16];
+        oz_tmem_ld16(taddr + d * OZ_BN, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fma(v[j], 128.0, oz_i2d(r[j]));
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double s0 = rs * __ldg(cs + c * 16 + 2 * j), s1 = rs * __ldg(cs + c * 16 + 2 * j + 1);
+        double2 out;
+        if (beta != 0.0) {
+          out.x = fma(v[2 * j], s0, beta * o[j].x);
+          out.y = fma(v[2 * j + 1], s1, beta * o[j].y);
+        } else {
+          out.x = v[2 * j] * s0;
+          out.y = v[2 * j + 1] * s1;
+        }
+        cp[j] = out;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(Cfg::TMEM_COLS));
+}
+
+// ---- slicing: one warp per row.  planes[s][row][k] (int8), sc[row] = 2^e -----------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(256)
+oz_slice_kernel(const double* __restrict__ P, int64_t ldp, int64_t rows, int32_t K, int8_t* __restrict__ planes,
+                int64_t plane_stride, double* __restrict__ sc) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const double* src = P + row * ldp;
+  double m = 0.0;
+  for (int k = lane * 4; k < K; k += 128) {
+    const double2 a = *reinterpret_cast<const double2*>(src + k), b = *reinterpret_cast<const double2*>(src + k + 2);
+    m = fmax(fmax(fabs(a.x), fabs(a.y)), fmax(m, fmax(fabs(b.x), fabs(b.y))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  int e = 0;
+  if (m > 0.0 && m < 1e300) {  // (inf / nan rows: the factorisation reports them through `info` anyway)
+    e = ilogb(m) + 1;
+    e = max(-1000, min(1000, e));
+  }
+  const double inv = __hiloint2double((1023 - e) << 20, 0);  // 2^-e
+  if (lane == 0) sc[row] = __hiloint2double((1023 + e) << 20, 0);
+  int8_t* dst = planes + row * K;
+  for (int k = lane * 4; k < K; k += 128) {
+    const double2 a = *reinterpret_cast<const double2*>(src + k), b = *reinterpret_cast<const double2*>(src + k + 2);
+    double r[4] = {a.x * inv, a.y * inv, b.x * inv, b.y * inv};
+    double pw = 64.0, ipw = 1.0 / 64.0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      char4 q;
+      double t;
+      t = rint(r[0] * pw); r[0] = fma(-t, ipw, r[0]); q.x = (signed char)(int)t;
+      t = rint(r[1] * pw); r[1] = fma(-t, ipw, r[1]); q.y = (signed char)(int)t;
+      t = rint(r[2] * pw); r[2] = fma(-t, ipw, r[2]); q.z = (signed char)(int)t;
+      t = rint(r[3] * pw); r[3] = fma(-t, ipw, r[3]); q.w = (signed char)(int)t;
+      *reinterpret_cast<char4*>(dst + (int64_t)s * plane_stride + k) = q;
+      pw *= 128.0;
+      ipw *= 1.0 / 128.0;
+    }
+  }
+}
+
+typedef CUresult (*OzEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+OzEncodeTiledFn oz_encode_fn() {
+  static OzEncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess)
+      return (OzEncodeTiledFn) nullptr;
+    return (OzEncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+bool oz_make_map(CUtensorMap* m, const int8_t* planes, int64_t K, int64_t rows_cap, int64_t plane_stride, int S,
+                 int box_rows) {
+  OzEncodeTiledFn enc = oz_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows_cap, (cuuint64_t)S};
+  cuuint64_t strides[2] = {(cuuint64_t)K, (cuuint64_t)plane_stride};
+  cuuint32_t box[3] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows, (cuuint32_t)S};
+  cuuint32_t es[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(planes), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int S>
+int oz_launch_slice(const double* P, int64_t ldp, int64_t rows, int64_t K, int8_t* planes, int64_t plane_stride, double* sc,
+                    cudaStream_t stream) {
+  if (rows == 0) return 0;
+  oz_slice_kernel<S><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(P, ldp, rows, (int32_t)K, planes, plane_stride, sc);
+  GPK_COUNT_LAUNCH();
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -1000 - (int)e;
+}
+
+template <int S>
+int oz_launch_gemm(int64_t M, int64_t N, int64_t K, double alpha, const int8_t* planesA, int64_t capA, int64_t strideA,
+                   const double* scA, int64_t rowA, const int8_t* planesB, int64_t capB, int64_t strideB,
+                   const double* scB, int64_t rowB, double beta, double* C, int64_t ldc, int32_t lower,
+                   cudaStream_t stream) {
+  CUtensorMap mA, mB;
+  if (!oz_make_map(&mA, planesA, K, capA, strideA, S, OZ_BM) || !oz_make_map(&mB, planesB, K, capB, strideB, S, OZ_BN))
+    return GPK_ERR_UNSUPPORTED;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(oz_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<S>::SMEM_BYTES);
+    if (e != cudaSuccess) return -1000 - (int)e;
+    attr_set = true;
+  }
+  OzParams p{alpha, beta, C, scA + rowA, scB + rowB, ldc, (int32_t)rowA, (int32_t)rowB, (int32_t)(K / OZ_BK), lower,
+             (int32_t)(M / OZ_BM), (int32_t)(N / OZ_BN)};
+  oz_gemm_kernel<S><<<(unsigned)(p.tiles_m * p.tiles_n), OZ_THREADS, OzCfg<S>::SMEM_BYTES, stream>>>(mA, mB, p);
+  GPK_COUNT_LAUNCH();
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -1000 - (int)e;
+}
+
+}  // namespace
+
+// ---- entry points used by potrf.cu and the C-ABI ----------------------------------------------------------------------
+// workspace for `rows` rows of K columns: S int8 planes [S][rows][K] followed by `rows` doubles (the row scales)
+int64_t oz_ws_bytes(int64_t rows, int64_t K, int32_t S) { return (int64_t)S * rows * K + rows * 8 + 256; }
+
+static inline double* oz_scales(void* ws, int64_t rows, int64_t K, int32_t S) {
+  const uintptr_t p = reinterpret_cast<uintptr_t>(ws) + (uintptr_t)((int64_t)S * rows * K);
+  return reinterpret_cast<double*>((p + 255) & ~uintptr_t(255));
+}
+
+int oz_slice_panel(const double* P, int64_t ldp, int64_t rows, int64_t K, void* ws, int64_t cap_rows, int32_t S,
+                   cudaStream_t stream) {
+  if (K % 128 || K > 65536 || rows > cap_rows || ldp % 2 || reinterpret_cast<uintptr_t>(P) % 16) return GPK_ERR_ARG;
+  int8_t* planes = static_cast<int8_t*>(ws);
+  double* sc = oz_scales(ws, cap_rows, K, S);
+  switch (S) {
+    case 5: return oz_launch_slice<5>(P, ldp, rows, K, planes, cap_rows * K, sc, stream);
+    case 6: return oz_launch_slice<6>(P, ldp, rows, K, planes, cap_rows * K, sc, stream);
+    case 7: return oz_launch_slice<7>(P, ldp, rows, K, planes, cap_rows * K, sc, stream);
+    case 8: return oz_launch_slice<8>(P, ldp, rows, K, planes, cap_rows * K, sc, stream);
+  }
+  return GPK_ERR_ARG;
+}
+
+// C[M x N] = beta C + alpha A B^T with A = sliced rows [rowA, rowA + M) of wsA, B = sliced rows [rowB, rowB + N) of wsB
+int oz_gemm_sliced(int64_t M, int64_t N, int64_t K, double alpha, const void* wsA, int64_t capA, int64_t rowA,
+                   const void* wsB, int64_t capB, int64_t rowB, double beta, double* C, int64_t ldc, int32_t lower,
+                   int32_t S, cudaStream_t stream) {
+  if (M % OZ_BM || N % OZ_BN || K % 128 || K > 65536 || ldc % 2 || reinterpret_cast<uintptr_t>(C) % 16) return GPK_ERR_ARG;
+  if (M == 0 || N == 0) return 0;
+  const int8_t* pa = static_cast<const int8_t*>(wsA);
+  const int8_t* pb = static_cast<const int8_t*>(wsB);
+  const double* sa = oz_scales(const_cast<void*>(wsA), capA, K, S);
+  const double* sb = oz_scales(const_cast<void*>(wsB), capB, K, S);
+#define OZ_CASE(SS)                                                                                                   \
+  case SS:                                                                                                            \
+    return oz_launch_gemm<SS>(M, N, K, alpha, pa, capA, capA * K, sa, rowA, pb, capB, capB * K, sb, rowB, beta, C, ldc, \
+                              lower, stream);
+  switch (S) {
+    OZ_CASE(5)
+    OZ_CASE(6)
+    OZ_CASE(7)
+    OZ_CASE(8)
+  }
+#undef OZ_CASE
+  return GPK_ERR_ARG;
+}
+
+}  // namespace gpk
+
+extern "C" {
+
+int64_t gpk_oz_ws_bytes(int64_t rows, int64_t K, int32_t slices) { return gpk::oz_ws_bytes(rows, K, slices); }
+
+int gpk_gemm_nt_f64_oz(int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, const double* B,
+                       int64_t ldb, double beta, double* C, int64_t ldc, int32_t lower, int32_t slices, void* ws,
+                       int64_t ws_bytes, void* stream) {
+  if (slices < 5 || slices > 8 || !ws) return GPK_ERR_ARG;
+  const int64_t need_a = gpk::oz_ws_bytes(M, K, slices), need_b = gpk::oz_ws_bytes(N, K, slices);
+  const bool same = (A == B && lda == ldb && M >= N);
+  const int64_t off_b = same ? 0 : ((need_a + 1023) & ~int64_t(1023));
+  if (ws_bytes < off_b + (same ? need_a : need_b) || reinterpret_cast<uintptr_t>(ws) % 1024) return GPK_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  void* wsb = static_cast<char*>(ws) + off_b;
+  if ((rc = gpk::oz_slice_panel(A, lda, M, K, ws, M, slices, s))) return rc;
+  if (!same && (rc = gpk::oz_slice_panel(B, ldb, N, K, wsb, N, slices, s))) return rc;
+  return gpk::oz_gemm_sliced(M, N, K, alpha, ws, M, 0, same ? ws : wsb, same ? M : N, 0, beta, C, ldc, lower, slices, s);
+}
+
+}  // extern "C"

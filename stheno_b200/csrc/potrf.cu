@@ -446,32 +446,71 @@ static int factor_panel(T* A, int64_t lda, int64_t a_bs, int64_t R, int64_t kb, 
 // SMs busy on the caller's stream.
 int syrk_f64_tf32x3(int64_t, int64_t, int64_t, const float*, double*, int64_t, cudaStream_t);  // gemm_tc32.cu
 int convert_panel_f32(const double*, int64_t, int64_t, int64_t, float*, cudaStream_t);
+int64_t oz_ws_bytes(int64_t rows, int64_t K, int32_t S);  // gemm_oz.cu
+int oz_slice_panel(const double*, int64_t, int64_t, int64_t, void*, int64_t, int32_t, cudaStream_t);
+int oz_gemm_sliced(int64_t, int64_t, int64_t, double, const void*, int64_t, int64_t, const void*, int64_t, int64_t, double,
+                   double*, int64_t, int32_t, int32_t, cudaStream_t);
 
-// trailing update C -= P P^T (lower tiles): fp64 DMMA by default; with a float workspace `ws` holding the fp32 copy of
-// the panel rows starting at `ws_row0`, the opt-in 3xTF32 tensor-core product.
+// How the K = NB_OUTER trailing updates of an fp64 factorisation are formed:
+//   MODE_F64     fp64 tensor cores (DMMA) straight from the matrix
+//   MODE_TF32X3  opt-in: fp32 copy of the panel, 3xTF32 products on tcgen05 (fp32-level products)
+//   MODE_OZAKI   int8 slices of the panel (error-free split), exact int32 products on tcgen05, fp64 recombination
+enum { MODE_F64 = 0, MODE_TF32X3 = 1, MODE_OZAKI = 2 };
+struct Trailing {
+  int mode = MODE_F64;
+  void* ws = nullptr;
+  int64_t ws_bytes = 0;
+  int32_t slices = 0;
+  int64_t cap_rows = 0;  // MODE_OZAKI: rows the workspace was laid out for
+};
+
+// Prepare the workspace copy of the panel rows [row0, row0 + rows) x [kb, kb + K) (row `i` of the copy = matrix row
+// row0 + i).  Returns the mode actually used for this panel.
 template <typename T>
-static int trailing_update(int64_t M, int64_t N, int64_t K, const T* P, int64_t lda, int64_t a_bs, T* C, int32_t batch,
-                           const float* ws_rows, cudaStream_t stream) {
+static int prepare_panel(const Trailing&, const T*, int64_t, int64_t, int64_t, int32_t, cudaStream_t, int* used) {
+  *used = MODE_F64;
+  return 0;
+}
+template <>
+int prepare_panel<double>(const Trailing& t, const double* P, int64_t ldp, int64_t rows, int64_t K, int32_t batch,
+                          cudaStream_t s, int* used) {
+  *used = MODE_F64;
+  if (t.mode == MODE_TF32X3 && batch == 1 && K % 32 == 0 && K >= 128 && t.ws_bytes >= rows * K * 4) {
+    *used = MODE_TF32X3;
+    return convert_panel_f32(P, ldp, rows, K, static_cast<float*>(t.ws), s);
+  }
+  if (t.mode == MODE_OZAKI && batch == 1 && K % 128 == 0 && rows <= t.cap_rows &&
+      t.ws_bytes >= oz_ws_bytes(t.cap_rows, K, t.slices)) {
+    *used = MODE_OZAKI;
+    return oz_slice_panel(P, ldp, rows, K, t.ws, t.cap_rows, t.slices, s);
+  }
+  return 0;
+}
+
+// trailing update C[M x N] (lower tiles) -= P[r0 : r0 + M] P[r0 : r0 + N]^T; `r0` = first row of the update relative to
+// the first row of the prepared panel copy.
+template <typename T>
+static int trailing_update(int used, const Trailing&, int64_t r0, int64_t M, int64_t N, int64_t K, const T* P, int64_t lda,
+                           int64_t a_bs, T* C, int32_t batch, cudaStream_t stream) {
   return gemm_nt(M, N, K, T(-1), P, lda, a_bs, P, lda, a_bs, T(1), C, lda, a_bs, 1, batch, stream);
 }
 template <>
-int trailing_update<double>(int64_t M, int64_t N, int64_t K, const double* P, int64_t lda, int64_t a_bs, double* C,
-                            int32_t batch, const float* ws_rows, cudaStream_t stream) {
-  if (ws_rows != nullptr) return syrk_f64_tf32x3(M, N, K, ws_rows, C, lda, stream);
+int trailing_update<double>(int used, const Trailing& t, int64_t r0, int64_t M, int64_t N, int64_t K, const double* P,
+                            int64_t lda, int64_t a_bs, double* C, int32_t batch, cudaStream_t stream) {
+  if (used == MODE_TF32X3) return syrk_f64_tf32x3(M, N, K, static_cast<const float*>(t.ws) + r0 * K, C, lda, stream);
+  if (used == MODE_OZAKI)
+    return oz_gemm_sliced(M, N, K, -1.0, t.ws, t.cap_rows, r0, t.ws, t.cap_rows, r0, 1.0, C, lda, 1, t.slices, stream);
   return gemm_nt(M, N, K, -1.0, P, lda, a_bs, P, lda, a_bs, 1.0, C, lda, a_bs, 1, batch, stream);
 }
-static int convert_panel(const double* P, int64_t ldp, int64_t rows, int64_t K, float* ws, cudaStream_t s) {
-  return convert_panel_f32(P, ldp, rows, K, ws, s);
-}
-static int convert_panel(const float*, int64_t, int64_t, int64_t, float*, cudaStream_t) { return 0; }
 
 template <typename T>
 static int potrf_driver(T* A, int64_t lda, int64_t a_bs, int64_t n_pad, int64_t extra_rows, T* logdet, int32_t* info,
-                        int32_t batch, cudaStream_t stream, float* ws = nullptr, int64_t ws_elems = 0) {
+                        int32_t batch, cudaStream_t stream, Trailing tr = Trailing()) {
   if (!A || n_pad < 0 || extra_rows < 0 || batch < 1 || !info) return GPK_ERR_ARG;
   if (n_pad % NB || extra_rows % NB || lda < n_pad) return GPK_ERR_ARG;
   if (lda % (16 / sizeof(T)) || reinterpret_cast<uintptr_t>(A) % 16) return GPK_ERR_ALIGN;
   const int64_t R = n_pad + extra_rows;
+  tr.cap_rows = R;
   int rc;
   Lookahead& la = lookahead();
   const bool use_la = la.ok && n_pad > 2 * NB_OUTER && getenv("GPK_NO_LOOKAHEAD") == nullptr;
@@ -483,34 +522,31 @@ static int potrf_driver(T* A, int64_t lda, int64_t a_bs, int64_t n_pad, int64_t 
     const int64_t ke = kb + NB_OUTER;                                   // panel [kb, ke) is factorised
     const int64_t ke2 = (ke + NB_OUTER < n_pad) ? ke + NB_OUTER : n_pad;  // next panel [ke, ke2)
     const int64_t K = ke - kb;
-    // opt-in mixed precision: fp32 copy of the panel rows [ke, R) for the tensor-core (3xTF32) trailing update
-    const bool mixed = ws != nullptr && sizeof(T) == 8 && batch == 1 && K % 32 == 0 && K >= 128 &&
-                       ws_elems >= (R - ke) * K;
-    if (mixed && (rc = convert_panel(A + ke * lda + kb, lda, R - ke, K, ws, stream))) return rc;
-    const bool more = ke2 < n_pad;
     const T* P = A + ke * lda + kb;
+    // reduced-cost arithmetic for the trailing update: workspace copy (fp32 / int8 slices) of the panel rows [ke, R)
+    int used = MODE_F64;
+    if ((rc = prepare_panel<T>(tr, P, lda, R - ke, K, batch, stream, &used))) return rc;
+    const bool more = ke2 < n_pad;
     if (use_la && more) {
       // side stream (high priority): (a) the next panel's columns, then that panel's factorisation;
       // caller's stream: (b) everything to the right of it.  (a) and (b) are independent (both only read panel i), so
       // they run concurrently and the short (a) no longer costs a kernel tail of its own.
       if ((rc = ce(cudaEventRecord(la.fork, stream)))) return rc;
       if ((rc = ce(cudaStreamWaitEvent(la.side, la.fork, 0)))) return rc;
-      if ((rc = trailing_update<T>(R - ke, ke2 - ke, K, P, lda, a_bs, A + ke * lda + ke, batch, mixed ? ws : nullptr,
-                                   la.side)))
+      if ((rc = trailing_update<T>(used, tr, 0, R - ke, ke2 - ke, K, P, lda, a_bs, A + ke * lda + ke, batch, la.side)))
         return rc;
       if ((rc = factor_panel<T>(A, lda, a_bs, R, ke, ke2, logdet, info, batch, la.side))) return rc;
       if ((rc = ce(cudaEventRecord(la.join, la.side)))) return rc;
-      if ((rc = trailing_update<T>(R - ke2, n_pad - ke2, K, A + ke2 * lda + kb, lda, a_bs, A + ke2 * lda + ke2, batch,
-                                   mixed ? ws + (ke2 - ke) * K : nullptr, stream)))
+      if ((rc = trailing_update<T>(used, tr, ke2 - ke, R - ke2, n_pad - ke2, K, A + ke2 * lda + kb, lda, a_bs,
+                                   A + ke2 * lda + ke2, batch, stream)))
         return rc;
       if ((rc = ce(cudaStreamWaitEvent(stream, la.join, 0)))) return rc;
     } else {
-      if ((rc = trailing_update<T>(R - ke, ke2 - ke, K, P, lda, a_bs, A + ke * lda + ke, batch, mixed ? ws : nullptr,
-                                   stream)))
+      if ((rc = trailing_update<T>(used, tr, 0, R - ke, ke2 - ke, K, P, lda, a_bs, A + ke * lda + ke, batch, stream)))
         return rc;
       if (more) {
-        if ((rc = trailing_update<T>(R - ke2, n_pad - ke2, K, A + ke2 * lda + kb, lda, a_bs, A + ke2 * lda + ke2, batch,
-                                     mixed ? ws + (ke2 - ke) * K : nullptr, stream)))
+        if ((rc = trailing_update<T>(used, tr, ke2 - ke, R - ke2, n_pad - ke2, K, A + ke2 * lda + kb, lda, a_bs,
+                                     A + ke2 * lda + ke2, batch, stream)))
           return rc;
       }
       if ((rc = factor_panel<T>(A, lda, a_bs, R, ke, ke2, logdet, info, batch, stream))) return rc;
@@ -590,14 +626,30 @@ static int trsm_right_t_driver(const T* L, int64_t ldl, int64_t l_bs, int64_t n_
 }  // namespace gpk
 
 extern "C" {
+int64_t gpk_potrf_oz_ws_bytes(int64_t n_pad, int64_t extra_rows, int32_t slices) {
+  return gpk::oz_ws_bytes(n_pad + extra_rows, gpk::nb_outer(), slices);
+}
 int gpk_potrf_f64(double* A, int64_t lda, int64_t a_bstride, int64_t n_pad, int64_t extra_rows, double* logdet,
                   int32_t* info, int32_t batch, void* stream) {
   return gpk::potrf_driver<double>(A, lda, a_bstride, n_pad, extra_rows, logdet, info, batch, (cudaStream_t)stream);
 }
 int gpk_potrf_f64_tf32x3(double* A, int64_t lda, int64_t a_bstride, int64_t n_pad, int64_t extra_rows, double* logdet,
                          int32_t* info, int32_t batch, float* ws, int64_t ws_elems, void* stream) {
-  return gpk::potrf_driver<double>(A, lda, a_bstride, n_pad, extra_rows, logdet, info, batch, (cudaStream_t)stream, ws,
-                                   ws_elems);
+  gpk::Trailing t;
+  t.mode = gpk::MODE_TF32X3;
+  t.ws = ws;
+  t.ws_bytes = ws_elems * 4;
+  return gpk::potrf_driver<double>(A, lda, a_bstride, n_pad, extra_rows, logdet, info, batch, (cudaStream_t)stream, t);
+}
+int gpk_potrf_f64_oz(double* A, int64_t lda, int64_t a_bstride, int64_t n_pad, int64_t extra_rows, double* logdet,
+                     int32_t* info, int32_t batch, int32_t slices, void* ws, int64_t ws_bytes, void* stream) {
+  if (slices < 5 || slices > 8 || !ws || reinterpret_cast<uintptr_t>(ws) % 1024) return GPK_ERR_ARG;
+  gpk::Trailing t;
+  t.mode = gpk::MODE_OZAKI;
+  t.ws = ws;
+  t.ws_bytes = ws_bytes;
+  t.slices = slices;
+  return gpk::potrf_driver<double>(A, lda, a_bstride, n_pad, extra_rows, logdet, info, batch, (cudaStream_t)stream, t);
 }
 int gpk_potrf_f32(float* A, int64_t lda, int64_t a_bstride, int64_t n_pad, int64_t extra_rows, float* logdet,
                   int32_t* info, int32_t batch, void* stream) {

@@ -351,10 +351,47 @@ def _potrf(W, n, n_pad, extra, k):
                                               B, _ptr(ws), ws.numel(), _stream())
         check(rc, "gpk_potrf_f64_tf32x3")
         return Chol(W, n, k, logdet, info)
+    slices = _oz_slices(getattr(_Bns, "precision", "fp64"))
+    if W.dtype == torch.float64 and B == 1 and slices and n_pad > 1024:
+        # fp64 emulated on the int8 tensor cores (error-free slicing, exact int32 products) for the trailing updates
+        lib = _lib.load()
+        ws = _aligned_bytes(lib.gpk_potrf_oz_ws_bytes(n_pad, extra, slices), W.device)
+        rc = lib.gpk_potrf_f64_oz(_ptr(W), W.stride(1), W.stride(0), n_pad, extra, _ptr(logdet), _ptr(info), B, slices,
+                                  _ptr(ws), ws.numel(), _stream())
+        check(rc, "gpk_potrf_f64_oz")
+        return Chol(W, n, k, logdet, info)
     rc = _fn("gpk_potrf", W.dtype)(_ptr(W), W.stride(1), W.stride(0), n_pad, extra, _ptr(logdet), _ptr(info), B,
                                    _stream())
     check(rc, "gpk_potrf")
     return Chol(W, n, k, logdet, info)
+
+
+def _oz_slices(precision):
+    """``B.precision`` -> number of int8 slices of the emulated trailing update (0: not emulated)."""
+    return {"int8x6": 6, "int8x7": 7, "int8x8": 8, "int8x5": 5}.get(precision, 0)
+
+
+def _aligned_bytes(nbytes, device, align=1024):
+    buf = torch.empty(int(nbytes) + align, device=device, dtype=torch.uint8)
+    off = (-buf.data_ptr()) % align
+    return buf[off : off + int(nbytes)]
+
+
+def gemm_nt_oz(A, Bm, C=None, *, alpha=1.0, beta=0.0, lower=False, slices=6):
+    """``C = beta C + alpha A B^T`` for fp64 row-major 2-D tensors through the int8 tensor-core emulation
+    (``gpk_gemm_nt_f64_oz``).  ``A: [M, K]``, ``Bm: [N, K]``; M % 128 == 0, N % 64 == 0, K % 128 == 0."""
+    _require_cuda(A, Bm, C)
+    M, K = A.shape
+    N = Bm.shape[0]
+    if C is None:
+        C = torch.zeros(M, N, device=A.device, dtype=A.dtype)
+    lib = _lib.load()
+    need = ((lib.gpk_oz_ws_bytes(M, K, slices) + 1023) // 1024) * 1024 + lib.gpk_oz_ws_bytes(N, K, slices)
+    ws = _aligned_bytes(need, A.device)
+    rc = lib.gpk_gemm_nt_f64_oz(M, N, K, float(alpha), _ptr(A), A.stride(0), _ptr(Bm), Bm.stride(0), float(beta), _ptr(C),
+                                C.stride(0), int(lower), int(slices), _ptr(ws), ws.numel(), _stream())
+    check(rc, "gpk_gemm_nt_f64_oz")
+    return C
 
 
 def chol_from_kernel(flat, xg, *, noise_scalar=0.0, noise_vec=None, jitter=0.0, rhs_t=None):
