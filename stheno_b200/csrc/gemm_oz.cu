@@ -9,10 +9,12 @@
 //
 // One 128 x 64 output tile per CTA; products with the same s + t share an accumulator: S accumulators x 64 TMEM columns.
 //   warp 0      TMA producer: per 64-byte k-block ONE box {64 B, 128 rows, S slices} of A and one {64 B, 64 rows, S} of B
-//               (cp.async.bulk.tensor.3d, SWIZZLE_64B, mbarrier complete_tx) into a 3- (S <= 6) or 2-stage ring
-//   warp 1      MMA issuer: S(S+1)/2 x 2 tcgen05.mma.kind::i8 (M=128, N=64, K=32) per k-block, tcgen05.commit per stage
+//               (cp.async.bulk.tensor.3d, SWIZZLE_64B, mbarrier complete_tx) into a 2-stage ring
+//   warp 1      MMA issuer: per K = 32 step slice s of A against slices 0..S-1-s of B as ONE tcgen05.mma.kind::i8 with
+//               N = 64 (S - s) (B slices adjacent in shared memory, accumulators adjacent in TMEM), tcgen05.commit per stage
 //   warps 2-5   epilogue: tcgen05.ld the S accumulators 16 columns at a time, Horner-combine them in fp64 (exact int32 ->
-//               double through the 2^52 trick), scale by 2^(e_row + e_col), C read-modify-write
+//               double through the 2^52 trick), scale by 2^(e_row + e_col), stage the row in shared memory and add it into
+//               C with a bulk reduce (cp.reduce.async.bulk .add.f64: the read-modify-write happens in L2, not in the SM)
 // The slicing kernel (oz_slice_kernel) is O(rows*K) and runs once per panel; in the Cholesky its output is shared by
 // every tile of the trailing update.
 //
@@ -35,19 +37,26 @@ struct OzCfg {
   static constexpr int A_BYTES = S * A_SLICE;
   static constexpr int B_BYTES = S * B_SLICE;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (3 * STAGE_BYTES + 1024 <= 227 * 1024) ? 3 : 2;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+  static constexpr int STAGES = 2;
+  // epilogue staging: 16 output columns (128 B) per row, pitch 144 B (36 words: conflict-free 16-byte stores from
+  // row-per-thread), ping-pong when it fits
+  static constexpr int OUT_PITCH = 144;
+  static constexpr int OUT_BYTES = OZ_BM * OUT_PITCH;  // 18 KB
+  static constexpr int OUT_BUFS = (STAGES * STAGE_BYTES + 2 * OUT_BYTES + 1024 <= 227 * 1024) ? 2 : 1;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BUFS * OUT_BYTES + 1024;
   static constexpr int TMEM_COLS = 512;  // S * 64 rounded up to a power of two (S = 5..8)
 };
 
 struct OzParams {
-  double alpha, beta;
+  double alpha;
   double* C;
   const double* sc_a;  // 2^e per A row (already offset to the first row of the problem)
   const double* sc_b;
   int64_t ldc;
   int32_t a_row0, b_row0;  // first plane row of A / B
   int32_t KB, lower, tiles_m, tiles_n;
+  int32_t total_tiles, tiles_per_cta, tri_rows;  // tri_rows: tile rows in the triangular part (lower mode)
+  int32_t accumulate;                            // 1: C += alpha A B^T (reduce-add), 0: C = alpha A B^T (store)
 };
 
 __device__ __forceinline__ void oz_mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -60,7 +69,11 @@ __device__ __forceinline__ void oz_mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra OZW_LOOP;\n"
       "OZW_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity));
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void oz_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void oz_tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
   asm volatile(
@@ -100,26 +113,44 @@ __device__ __forceinline__ void oz_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) 
 __device__ __forceinline__ double oz_i2d(uint32_t x) {
   return __hiloint2double(0x43300000, (int)(x ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
 }
+// tile index -> (tile row, tile column).  Lower mode enumerates only the tiles that touch the lower triangle, row by row:
+// row tm holds min(tiles_n, 2 (tm + 1)) tiles (128 x 64 tiles), i.e. tm (tm + 1) tiles precede row tm while tm <= tri_rows.
+__device__ __forceinline__ void oz_tile(const OzParams& p, int t, int& tm, int& tn) {
+  if (!p.lower) {
+    tm = t / p.tiles_n;
+    tn = t - tm * p.tiles_n;
+    return;
+  }
+  const int tri = p.tri_rows * (p.tri_rows + 1);
+  if (t < tri) {
+    tm = (int)((sqrtf(4.f * (float)t + 1.f) - 1.f) * 0.5f);
+    while (tm * (tm + 1) > t) --tm;
+    while ((tm + 1) * (tm + 2) <= t) ++tm;
+    tn = t - tm * (tm + 1);
+  } else {
+    const int r = t - tri;
+    tm = p.tri_rows + r / p.tiles_n;
+    tn = r - (tm - p.tri_rows) * p.tiles_n;
+  }
+}
 
+// One CTA works through `tiles_per_cta` consecutive tiles: the TMA producer and the MMA issuer run ahead into the next tile
+// while the epilogue warps drain the accumulators of the previous one (TMEM full / empty barriers), and the update of C
+// itself leaves the SM asynchronously (bulk reduce-add from the staging buffer), overlapping the next main loop.  CTAs stay
+// short-lived (a few tiles) on purpose: the Cholesky's look-ahead stream needs SMs to come free every few tens of us.
 template <int S>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const OzParams p) {
   using Cfg = OzCfg<S>;
   constexpr int STAGES = Cfg::STAGES;
-  int tm, tn;
-  {
-    const int GROUP = 8, per_group = GROUP * p.tiles_n, id = blockIdx.x;
-    const int group = id / per_group, first_m = group * GROUP, gsize = min(p.tiles_m - first_m, GROUP);
-    const int r = id - group * per_group;
-    tm = first_m + r % gsize;
-    tn = r / gsize;
-  }
-  if (p.lower && tn * OZ_BN >= (tm + 1) * OZ_BM) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t_begin = blockIdx.x * p.tiles_per_cta;
+  const int t_end = min(t_begin + p.tiles_per_cta, p.total_tiles);
 
   extern __shared__ uint8_t oz_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  uint8_t* out_smem = smem + STAGES * Cfg::STAGE_BYTES;
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar, tmem_empty_bar;
   __shared__ uint32_t tmem_base_holder;
 
   if (warp == 0) {
@@ -132,7 +163,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&accum_bar, 1);
+    mbar_init(&tmem_full_bar, 1);
+    mbar_init(&tmem_empty_bar, 128);
     fence_mbar_init();
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
@@ -143,91 +175,118 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % STAGES, it = kb / STAGES;
-        if (it > 0) oz_mbar_wait(&empty_bar[s], (it - 1) & 1);
-        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        oz_tma_load_3d(st, &mapA, kb * OZ_BK, p.a_row0 + tm * OZ_BM, 0, &full_bar[s]);
-        oz_tma_load_3d(st + Cfg::A_BYTES, &mapB, kb * OZ_BK, p.b_row0 + tn * OZ_BN, 0, &full_bar[s]);
+      int g = 0;  // k-blocks issued so far (all tiles)
+      for (int t = t_begin; t < t_end; ++t) {
+        int tm, tn;
+        oz_tile(p, t, tm, tn);
+        for (int kb = 0; kb < KB; ++kb, ++g) {
+          const int s = g % STAGES, it = g / STAGES;
+          if (it > 0) oz_mbar_wait(&empty_bar[s], (it - 1) & 1);
+          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          oz_tma_load_3d(st, &mapA, kb * OZ_BK, p.a_row0 + tm * OZ_BM, 0, &full_bar[s]);
+          oz_tma_load_3d(st + Cfg::A_BYTES, &mapB, kb * OZ_BK, p.b_row0 + tn * OZ_BN, 0, &full_bar[s]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor: D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), K-major, N >> 3 at 17, M >> 4 at 24
-      const uint32_t idesc =
-          (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % STAGES, it = kb / STAGES;
-        oz_mbar_wait(&full_bar[s], it & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
-        const uint32_t a0 = smem_u32(smem + s * Cfg::STAGE_BYTES), b0 = a0 + Cfg::A_BYTES;
+      const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
+      int g = 0;
+      for (int t = t_begin, ti = 0; t < t_end; ++t, ++ti) {
+        if (ti > 0) {  // the epilogue must have drained the previous tile's accumulators
+          oz_mbar_wait(&tmem_empty_bar, (ti - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+        }
+        for (int kb = 0; kb < KB; ++kb, ++g) {
+          const int s = g % STAGES, it = g / STAGES;
+          oz_mbar_wait(&full_bar[s], it & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+          const uint32_t a0 = smem_u32(smem + s * Cfg::STAGE_BYTES), b0 = a0 + Cfg::A_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {  // UMMA K = 32 int8 = 32 bytes inside the 64-byte swizzle row
+          for (int ks = 0; ks < 2; ++ks) {  // UMMA K = 32 int8 = 32 bytes inside the 64-byte swizzle row
+            // Slice sa of A meets slices 0 .. S-1-sa of B, whose products go to the ADJACENT accumulators sa .. S-1: the B
+            // slices are contiguous in shared memory (64 rows each) and the accumulators contiguous in TMEM (64 columns
+            // each), so they are ONE MMA with N = 64 (S - sa) (split at the N = 256 limit) -- A is read from shared memory
+            // 8 times per K step instead of 21 (S = 6), which takes the kernel off the shared-memory bandwidth limit.
 #pragma unroll
-          for (int sa = 0; sa < S; ++sa) {
+            for (int sa = 0; sa < S; ++sa) {
 #pragma unroll
-            for (int sb = 0; sb + sa < S; ++sb) {
-              oz_umma_i8(tmem + (uint32_t)((sa + sb) * OZ_BN), oz_desc(a0 + sa * Cfg::A_SLICE + ks * 32),
-                         oz_desc(b0 + sb * Cfg::B_SLICE + ks * 32), idesc, (kb > 0 || ks > 0 || sa > 0) ? 1u : 0u);
+              for (int sb = 0; sb + sa < S; sb += 4) {
+                const int nsl = (S - sa - sb) < 4 ? (S - sa - sb) : 4;  // B slices in this MMA
+                const uint32_t idesc = idesc0 | ((uint32_t)((nsl * OZ_BN) >> 3) << 17);
+                oz_umma_i8(tmem + (uint32_t)((sa + sb) * OZ_BN), oz_desc(a0 + sa * Cfg::A_SLICE + ks * 32),
+                           oz_desc(b0 + sb * Cfg::B_SLICE + ks * 32), idesc, (kb > 0 || ks > 0 || sa > 0) ? 1u : 0u);
+              }
             }
           }
+          oz_umma_commit(&empty_bar[s]);
         }
-        oz_umma_commit(&empty_bar[s]);
+        oz_umma_commit(&tmem_full_bar);
       }
-      oz_umma_commit(&accum_bar);
     }
   } else {
-    // ---- epilogue: TMEM -> registers -> fp64 combine -> C (read-modify-write) ----
+    // ---- epilogue: TMEM -> registers -> fp64 combine -> staging row in shared memory -> bulk reduce-add into C ----
     const int lane_group = warp & 3;  // a warp may only touch TMEM lanes 32 * (warp % 4) .. + 31
     const int row = lane_group * 32 + lane;
     // 2^-(12 + 7 (S-1)): weight of the last kept diagonal; Horner runs from diagonal 0 (largest weight) down
     const double w_last = __hiloint2double((1023 - (12 + 7 * (S - 1))) << 20, 0);
-    const double rs = p.alpha * w_last * __ldg(p.sc_a + (int64_t)tm * OZ_BM + row);
-    const double* cs = p.sc_b + (int64_t)tn * OZ_BN;
-    double* Crow = p.C + ((int64_t)tm * OZ_BM + row) * p.ldc + (int64_t)tn * OZ_BN;
-    const double beta = p.beta;
-    oz_mbar_wait(&accum_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
-#pragma unroll 1
-    for (int c = 0; c < OZ_BN / 16; ++c) {
-      double2 o[8];
-      double2* cp = reinterpret_cast<double2*>(Crow + c * 16);
-      if (beta != 0.0) {
+    int chunk = 0;  // staging chunks issued by this thread so far
+    for (int t = t_begin, ti = 0; t < t_end; ++t, ++ti) {
+      int tm, tn;
+      oz_tile(p, t, tm, tn);
+      const double rs = p.alpha * w_last * __ldg(p.sc_a + (int64_t)tm * OZ_BM + row);
+      const double* cs = p.sc_b + (int64_t)tn * OZ_BN;
+      double* Crow = p.C + ((int64_t)tm * OZ_BM + row) * p.ldc + (int64_t)tn * OZ_BN;
+      oz_mbar_wait(&tmem_full_bar, ti & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = cp[j];
-      }
-      double v[16];
-      const uint32_t taddr = tmem + ((uint32_t)(lane_group * 32) << 16) + c * 16;
-      {
-        uint32_t r[16];
-        oz_tmem_ld16(taddr, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::);
+      for (int c = 0; c < OZ_BN / 16; ++c, ++chunk) {
+        const uint32_t taddr = tmem + ((uint32_t)(lane_group * 32) << 16) + c * 16;
+        uint32_t r[S][16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = oz_i2d(r[j]);
-      }
-#pragma unroll
-      for (int d = 1; d < S; ++d) {
-        uint32_t r[16];
-        oz_tmem_ld16(taddr + d * OZ_BN, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fma(v[j], 128.0, oz_i2d(r[j]));
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const double s0 = rs * __ldg(cs + c * 16 + 2 * j), s1 = rs * __ldg(cs + c * 16 + 2 * j + 1);
-        double2 out;
-        if (beta != 0.0) {
-          out.x = fma(v[2 * j], s0, beta * o[j].x);
-          out.y = fma(v[2 * j + 1], s1, beta * o[j].y);
-        } else {
-          out.x = v[2 * j] * s0;
-          out.y = v[2 * j + 1] * s1;
+        for (int d = 0; d < S; ++d) oz_tmem_ld16(taddr + d * OZ_BN, r[d]);  // all S accumulators in flight, one wait
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        if (c == OZ_BN / 16 - 1) {  // the accumulators of this tile are in registers: hand TMEM back to the MMA issuer
+          asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+          oz_mbar_arrive(&tmem_empty_bar);
         }
-        cp[j] = out;
+        double v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = oz_i2d(r[0][j]);
+#pragma unroll
+        for (int d = 1; d < S; ++d) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fma(v[j], 128.0, oz_i2d(r[d][j]));
+        }
+        // this thread's staging row (its own bulk operations are the only readers, so no CTA-level barrier is needed):
+        // wait until the bulk operation that last read this buffer has finished reading it
+        uint8_t* stg = out_smem + (Cfg::OUT_BUFS == 2 ? (chunk & 1) * Cfg::OUT_BYTES : 0) + row * Cfg::OUT_PITCH;
+        if (Cfg::OUT_BUFS == 2)
+          asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+        else
+          asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          double2 out;
+          out.x = v[2 * j] * (rs * __ldg(cs + c * 16 + 2 * j));
+          out.y = v[2 * j + 1] * (rs * __ldg(cs + c * 16 + 2 * j + 1));
+          reinterpret_cast<double2*>(stg)[j] = out;
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the bulk (async-proxy) read
+        if (p.accumulate)
+          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 128;\n" ::"l"(Crow + c * 16),
+                       "r"(smem_u32(stg))
+                       : "memory");
+        else
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;\n" ::"l"(Crow + c * 16),
+                       "r"(smem_u32(stg))
+                       : "memory");
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
       }
     }
+    asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
   __syncthreads();
@@ -315,6 +374,11 @@ int oz_launch_slice(const double* P, int64_t ldp, int64_t rows, int64_t K, int8_
   return e == cudaSuccess ? 0 : -1000 - (int)e;
 }
 
+__global__ void oz_scale_kernel(double* C, int64_t ldc, int64_t M, int64_t N, double beta) {
+  const int64_t i = (int64_t)blockIdx.y, j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M && j < N) C[i * ldc + j] *= beta;
+}
+
 template <int S>
 int oz_launch_gemm(int64_t M, int64_t N, int64_t K, double alpha, const int8_t* planesA, int64_t capA, int64_t strideA,
                    const double* scA, int64_t rowA, const int8_t* planesB, int64_t capB, int64_t strideB,
@@ -330,9 +394,20 @@ int oz_launch_gemm(int64_t M, int64_t N, int64_t K, double alpha, const int8_t* 
     if (e != cudaSuccess) return -1000 - (int)e;
     attr_set = true;
   }
-  OzParams p{alpha, beta, C, scA + rowA, scB + rowB, ldc, (int32_t)rowA, (int32_t)rowB, (int32_t)(K / OZ_BK), lower,
-             (int32_t)(M / OZ_BM), (int32_t)(N / OZ_BN)};
-  oz_gemm_kernel<S><<<(unsigned)(p.tiles_m * p.tiles_n), OZ_THREADS, OzCfg<S>::SMEM_BYTES, stream>>>(mA, mB, p);
+  if (beta != 0.0 && beta != 1.0) {  // the kernel adds into C (or overwrites it): apply any other beta first
+    if (M > 65535) return GPK_ERR_UNSUPPORTED;
+    oz_scale_kernel<<<dim3((unsigned)((N + 255) / 256), (unsigned)M), 256, 0, stream>>>(C, ldc, M, N, beta);
+    GPK_COUNT_LAUNCH();
+  }
+  const int32_t tiles_m = (int32_t)(M / OZ_BM), tiles_n = (int32_t)(N / OZ_BN);
+  const int32_t tri_rows = lower ? (tiles_m < tiles_n / 2 ? tiles_m : tiles_n / 2) : 0;
+  const int32_t total = lower ? tri_rows * (tri_rows + 1) + (tiles_m - tri_rows) * tiles_n : tiles_m * tiles_n;
+  static const int force_tpc = getenv("GPK_OZ_TPC") ? atoi(getenv("GPK_OZ_TPC")) : 0;
+  int32_t tpc = force_tpc > 0 ? force_tpc : total / 296;  // >= 2 waves of CTAs over 148 SMs before CTAs grow
+  tpc = tpc < 1 ? 1 : (tpc > 4 && force_tpc <= 0 ? 4 : tpc);
+  OzParams p{alpha, C, scA + rowA, scB + rowB, ldc, (int32_t)rowA, (int32_t)rowB, (int32_t)(K / OZ_BK), lower,
+             tiles_m, tiles_n, total, tpc, tri_rows, beta != 0.0 ? 1 : 0};
+  oz_gemm_kernel<S><<<(unsigned)((total + tpc - 1) / tpc), OZ_THREADS, OzCfg<S>::SMEM_BYTES, stream>>>(mA, mB, p);
   GPK_COUNT_LAUNCH();
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -1000 - (int)e;
