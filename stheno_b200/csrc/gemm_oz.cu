@@ -13,8 +13,9 @@
 //   warp 1      MMA issuer: per K = 32 step slice s of A against slices 0..S-1-s of B as ONE tcgen05.mma.kind::i8 with
 //               N = 64 (S - s) (B slices adjacent in shared memory, accumulators adjacent in TMEM), tcgen05.commit per stage
 //   warps 2-5   epilogue: tcgen05.ld the S accumulators 16 columns at a time, Horner-combine them in fp64 (exact int32 ->
-//               double through the 2^52 trick), scale by 2^(e_row + e_col), stage the row in shared memory and add it into
-//               C with a bulk reduce (cp.reduce.async.bulk .add.f64: the read-modify-write happens in L2, not in the SM)
+//               double through the 2^52 trick), scale by 2^(e_row + e_col), stage 128 x 16 boxes in shared memory and add
+//               them into C with TMA tensor reduces (cp.reduce.async.bulk.tensor .add, fp64 tensor map: the
+//               read-modify-write of C happens in L2, not in the SM)
 // The slicing kernel (oz_slice_kernel) is O(rows*K) and runs once per panel; in the Cholesky its output is shared by
 // every tile of the trailing update.
 //
@@ -38,11 +39,11 @@ struct OzCfg {
   static constexpr int B_BYTES = S * B_SLICE;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = 2;
-  // epilogue staging: 16 output columns (128 B) per row, pitch 144 B (36 words: conflict-free 16-byte stores from
-  // row-per-thread), ping-pong when it fits
-  static constexpr int OUT_PITCH = 144;
-  static constexpr int OUT_BYTES = OZ_BM * OUT_PITCH;  // 18 KB
-  static constexpr int OUT_BUFS = (STAGES * STAGE_BYTES + 2 * OUT_BYTES + 1024 <= 227 * 1024) ? 2 : 1;
+  // epilogue staging: one 128 x 16 fp64 box (16 KB, SWIZZLE_128B so that row-per-thread 16-byte stores are conflict-free)
+  // per TMA tensor reduce; ping-pong when it fits next to the ring
+  static constexpr int OUT_BYTES = OZ_BM * 128;
+  static constexpr int SMEM_MAX = 226 * 1024;  // 227 KB per CTA minus the static barriers / alignment slack
+  static constexpr int OUT_BUFS = (STAGES * STAGE_BYTES + 2 * OUT_BYTES + 1024 <= SMEM_MAX) ? 2 : 1;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BUFS * OUT_BYTES + 1024;
   static constexpr int TMEM_COLS = 512;  // S * 64 rounded up to a power of two (S = 5..8)
 };
@@ -140,7 +141,8 @@ __device__ __forceinline__ void oz_tile(const OzParams& p, int t, int& tm, int& 
 // short-lived (a few tiles) on purpose: the Cholesky's look-ahead stream needs SMs to come free every few tens of us.
 template <int S>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
-oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const OzParams p) {
+oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapC, const OzParams p) {
   using Cfg = OzCfg<S>;
   constexpr int STAGES = Cfg::STAGES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -232,58 +234,73 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int row = lane_group * 32 + lane;
     // 2^-(12 + 7 (S-1)): weight of the last kept diagonal; Horner runs from diagonal 0 (largest weight) down
     const double w_last = __hiloint2double((1023 - (12 + 7 * (S - 1))) << 20, 0);
-    int chunk = 0;  // staging chunks issued by this thread so far
+    const bool elected = threadIdx.x == 64;
+    int chunk = 0;  // boxes staged so far
     for (int t = t_begin, ti = 0; t < t_end; ++t, ++ti) {
       int tm, tn;
       oz_tile(p, t, tm, tn);
       const double rs = p.alpha * w_last * __ldg(p.sc_a + (int64_t)tm * OZ_BM + row);
       const double* cs = p.sc_b + (int64_t)tn * OZ_BN;
-      double* Crow = p.C + ((int64_t)tm * OZ_BM + row) * p.ldc + (int64_t)tn * OZ_BN;
       oz_mbar_wait(&tmem_full_bar, ti & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+      // (1) drain: all 64 columns of this row, Horner-combined on the fly (diagonal 0 carries the largest weight), then hand
+      //     TMEM back so that the next tile's MMAs overlap everything below
+      double v[OZ_BN];
+#pragma unroll
+      for (int c = 0; c < OZ_BN / 16; ++c) {
+        const uint32_t taddr = tmem + ((uint32_t)(lane_group * 32) << 16) + c * 16;
+#pragma unroll
+        for (int d0 = 0; d0 < S; d0 += 4) {
+          constexpr int G = 4;
+          uint32_t r[G][16];
+#pragma unroll
+          for (int d = d0; d < d0 + G && d < S; ++d) oz_tmem_ld16(taddr + d * OZ_BN, r[d - d0]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+          for (int d = d0; d < d0 + G && d < S; ++d) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              v[c * 16 + j] = (d == 0) ? oz_i2d(r[0][j]) : fma(v[c * 16 + j], 128.0, oz_i2d(r[d - d0][j]));
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+      oz_mbar_arrive(&tmem_empty_bar);
+      // (2) scale and stage 16 columns of all 128 rows (one 16 KB box, 128-byte swizzle), then ONE thread adds the box into C
+      //     with a TMA tensor reduce (cp.reduce.async.bulk.tensor .add on an fp64 tensor map: the read-modify-write of C
+      //     happens in L2).  All of this overlaps the next tile's main loop.
 #pragma unroll
       for (int c = 0; c < OZ_BN / 16; ++c, ++chunk) {
-        const uint32_t taddr = tmem + ((uint32_t)(lane_group * 32) << 16) + c * 16;
-        uint32_t r[S][16];
-#pragma unroll
-        for (int d = 0; d < S; ++d) oz_tmem_ld16(taddr + d * OZ_BN, r[d]);  // all S accumulators in flight, one wait
-        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-        if (c == OZ_BN / 16 - 1) {  // the accumulators of this tile are in registers: hand TMEM back to the MMA issuer
-          asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
-          oz_mbar_arrive(&tmem_empty_bar);
+        uint8_t* buf = out_smem + (Cfg::OUT_BUFS == 2 ? (chunk & 1) * Cfg::OUT_BYTES : 0);
+        if (elected) {  // the reduce that last used this buffer has finished reading it
+          if (Cfg::OUT_BUFS == 2)
+            asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+          else
+            asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
         }
-        double v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = oz_i2d(r[0][j]);
-#pragma unroll
-        for (int d = 1; d < S; ++d) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fma(v[j], 128.0, oz_i2d(r[d][j]));
-        }
-        // this thread's staging row (its own bulk operations are the only readers, so no CTA-level barrier is needed):
-        // wait until the bulk operation that last read this buffer has finished reading it
-        uint8_t* stg = out_smem + (Cfg::OUT_BUFS == 2 ? (chunk & 1) * Cfg::OUT_BYTES : 0) + row * Cfg::OUT_PITCH;
-        if (Cfg::OUT_BUFS == 2)
-          asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
-        else
-          asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+          const int col = c * 16 + 2 * j;
           double2 out;
-          out.x = v[2 * j] * (rs * __ldg(cs + c * 16 + 2 * j));
-          out.y = v[2 * j + 1] * (rs * __ldg(cs + c * 16 + 2 * j + 1));
-          reinterpret_cast<double2*>(stg)[j] = out;
+          out.x = v[col] * (rs * __ldg(cs + col));
+          out.y = v[col + 1] * (rs * __ldg(cs + col + 1));
+          *reinterpret_cast<double2*>(buf + row * 128 + ((j ^ (row & 7)) << 4)) = out;
         }
-        fence_proxy_async();  // generic-proxy writes -> visible to the bulk (async-proxy) read
-        if (p.accumulate)
-          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 128;\n" ::"l"(Crow + c * 16),
-                       "r"(smem_u32(stg))
-                       : "memory");
-        else
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;\n" ::"l"(Crow + c * 16),
-                       "r"(smem_u32(stg))
-                       : "memory");
-        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async-proxy) read
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        if (elected) {
+          if (p.accumulate)
+            asm volatile(
+                "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(&mapC),
+                "r"(tn * OZ_BN + c * 16), "r"(tm * OZ_BM), "r"(smem_u32(buf))
+                : "memory");
+          else
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(&mapC),
+                         "r"(tn * OZ_BN + c * 16), "r"(tm * OZ_BM), "r"(smem_u32(buf))
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        }
       }
     }
     asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
@@ -384,9 +401,18 @@ int oz_launch_gemm(int64_t M, int64_t N, int64_t K, double alpha, const int8_t* 
                    const double* scA, int64_t rowA, const int8_t* planesB, int64_t capB, int64_t strideB,
                    const double* scB, int64_t rowB, double beta, double* C, int64_t ldc, int32_t lower,
                    cudaStream_t stream) {
-  CUtensorMap mA, mB;
+  CUtensorMap mA, mB, mC;
   if (!oz_make_map(&mA, planesA, K, capA, strideA, S, OZ_BM) || !oz_make_map(&mB, planesB, K, capB, strideB, S, OZ_BN))
     return GPK_ERR_UNSUPPORTED;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)ldc * 8};
+    cuuint32_t box[2] = {16, (cuuint32_t)OZ_BM}, es[2] = {1, 1};
+    if (oz_encode_fn()(&mC, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, C, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return GPK_ERR_UNSUPPORTED;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
@@ -407,7 +433,7 @@ int oz_launch_gemm(int64_t M, int64_t N, int64_t K, double alpha, const int8_t* 
   tpc = tpc < 1 ? 1 : (tpc > 4 && force_tpc <= 0 ? 4 : tpc);
   OzParams p{alpha, C, scA + rowA, scB + rowB, ldc, (int32_t)rowA, (int32_t)rowB, (int32_t)(K / OZ_BK), lower,
              tiles_m, tiles_n, total, tpc, tri_rows, beta != 0.0 ? 1 : 0};
-  oz_gemm_kernel<S><<<(unsigned)((total + tpc - 1) / tpc), OZ_THREADS, OzCfg<S>::SMEM_BYTES, stream>>>(mA, mB, p);
+  oz_gemm_kernel<S><<<(unsigned)((total + tpc - 1) / tpc), OZ_THREADS, OzCfg<S>::SMEM_BYTES, stream>>>(mA, mB, mC, p);
   GPK_COUNT_LAUNCH();
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -1000 - (int)e;
