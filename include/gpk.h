@@ -149,6 +149,15 @@ int gpk_potrf_f64_tf32x3(double* A, int64_t lda, int64_t a_bstride, int64_t n_pa
 int64_t gpk_potrf_oz_ws_bytes(int64_t n_pad, int64_t extra_rows, int32_t slices);
 int gpk_potrf_f64_oz(double* A, int64_t lda, int64_t a_bstride, int64_t n_pad, int64_t extra_rows, double* logdet,
                      int32_t* info, int32_t batch, int32_t slices, void* ws, int64_t ws_bytes, void* stream);
+/* Library-wide switch (like cublasSetMathMode), per host thread and device: with slices = 5..8 and a caller-owned, 1024-byte
+ * aligned scratch buffer, the LARGE fp64 GEMM-shaped updates inside gpk_potrf_f64 (trailing updates, n_pad >= 2048),
+ * gpk_trsm_right_f64 and gpk_gemm_nt_f64 (batch 1, M, N >= 256, M N K >= 1.5e9, K <= 65536) run on the int8 tensor cores
+ * whenever the scratch is large enough (gpk_f64_emulation_scratch_bytes for a GEMM, gpk_potrf_oz_ws_bytes for a
+ * factorisation); everything else stays on the fp64 tensor cores.  slices = 0 switches it off.  Calls that use the scratch
+ * must be stream-ordered with respect to each other. */
+int gpk_set_f64_emulation(int32_t slices, void* scratch, int64_t scratch_bytes);
+int64_t gpk_f64_emulation_scratch_bytes(int64_t M, int64_t N, int64_t K, int32_t slices);
+
 /* The emulated GEMM on its own: C = beta C + alpha A B^T (M % 128 == 0, N % 64 == 0, K % 128 == 0, K <= 65536).
  * `ws`: 1024-byte aligned, >= round_up(gpk_oz_ws_bytes(M, K, slices), 1024) + gpk_oz_ws_bytes(N, K, slices) bytes. */
 int64_t gpk_oz_ws_bytes(int64_t rows, int64_t K, int32_t slices);
@@ -213,6 +222,7 @@ double gpk_probe_dmma_tflops(void);
  * summed durations, the summed ALGORITHMIC flops (2*128*128*K per computed tile) and the launch count.
  * enable(0/1) also clears the record. */
 void gpk_gemm_profile_enable(int32_t on);
+int gpk_gemm_profile_read_kind(int32_t kind, double* total_ms, double* total_flops, int64_t* launches); /* 0 DMMA, 1 int8 emulation, -1 all */
 int gpk_gemm_profile_read(double* total_ms_host, double* total_flops_host, int64_t* launches_host);
 
 /* Number of kernels this library has launched since load / the last reset (bench.py's `gpu_launches`). */

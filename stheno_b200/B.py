@@ -7,10 +7,17 @@ import torch
 #: examples raise it to 1e-6 for float32 (``README.md:983``).
 epsilon = 1e-12
 
-#: Arithmetic of the Cholesky trailing update for float64 problems.  "fp64" (default): fp64 tensor cores (DMMA), meets
-#: the 1e-10 parity bar.  "tf32x3" (opt-in): fp32 panel copy + 3xTF32 products on the tcgen05 tensor cores, fp64
-#: accumulation into the matrix -- ~2x faster, agrees to ~1e-6 relative.
-precision = "fp64"
+#: Arithmetic of the LARGE GEMM-shaped updates of float64 problems (Cholesky trailing updates for n >= 2048, the GEMMs of
+#: the triangular solves and ``gemm_nt`` with M N K >= 1.5e9; single-matrix problems).  Everything else -- kernel-matrix
+#: build, leaf factorisations, panel solves, small problems, batched problems -- always runs in native fp64.
+#:   "auto" (default) = "int8x7": fp64 emulated on the int8 tensor cores (tcgen05.mma.kind::i8): operands split error-free
+#:       into 7 signed 7-bit slices (49 bits), EXACT int32 slice products, fp64 recombination.  Product error ~3e-14 |a||b|;
+#:       log-pdfs agree with the native path to ~1e-13 relative -- three orders inside the 1e-10 parity bar.  ~2x faster.
+#:   "int8x8": 8 slices (56 bits >= the 53 of fp64): product error ~1e-15, the same as the fp64 tensor-core kernel itself.
+#:   "int8x6": 6 slices (42 bits): ~4e-12 products, log-pdfs ~4e-10 -- faster still, NOT inside the parity bar.
+#:   "fp64": native fp64 tensor cores (DMMA) everywhere.
+#:   "tf32x3" (opt-in, north_star "tf32/bf16 where the user opts in"): fp32 panel copy + 3xTF32 products, ~1e-6 relative.
+precision = "auto"
 
 pi = np.pi
 log_2_pi = float(np.log(2 * np.pi))

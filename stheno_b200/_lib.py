@@ -60,10 +60,13 @@ _PLAIN = {
     "gpk_potrf_oz_ws_bytes": ([_i64, _i64, _i32], _i64),
     "gpk_potrf_f64_oz": ([_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _i32, _i32, _ptr, _i64, _ptr], c_int32),
     "gpk_oz_ws_bytes": ([_i64, _i64, _i32], _i64),
+    "gpk_set_f64_emulation": ([_i32, _ptr, _i64], c_int32),
+    "gpk_f64_emulation_scratch_bytes": ([_i64, _i64, _i64, _i32], _i64),
     "gpk_gemm_nt_f64_oz": ([_i64, _i64, _i64, _f64, _ptr, _i64, _ptr, _i64, _f64, _ptr, _i64, _i32, _i32, _ptr, _i64,
                             _ptr], c_int32),
     "gpk_gemm_profile_enable": ([_i32], None),
     "gpk_gemm_profile_read": ([POINTER(c_double), POINTER(c_double), POINTER(_i64)], c_int32),
+    "gpk_gemm_profile_read_kind": ([_i32, POINTER(c_double), POINTER(c_double), POINTER(_i64)], c_int32),
 }
 
 #: every symbol ``include/gpk.h`` declares (checked by tests/test_abi.py against the header text)

@@ -68,6 +68,14 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+// fp64 emulation mode set by the caller through gpk_set_f64_emulation (gemm_oz.cu), per host thread and device
+struct Emulation {
+  int32_t slices = 0;
+  void* scratch = nullptr;
+  int64_t bytes = 0;
+};
+Emulation& emulation();
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

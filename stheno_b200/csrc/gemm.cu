@@ -548,22 +548,29 @@ static int check_gemm_args(int64_t M, int64_t N, int64_t K, const T* A, int64_t 
 // ---- in-situ timing of the dominant kernel (bench.py's roofline leg) ----------------------------------------------
 // When enabled, every fp64 GEMM launch is bracketed by two events on ITS OWN stream; gpk_gemm_profile_read() sums the
 // elapsed times and the algorithmic flops (2 * 128 * 128 * K per computed tile) after the caller has synchronised.
+// kind 0: fp64 DMMA trailing-update GEMM (v3 kernel); kind 1: int8-slice emulation GEMM (gemm_oz.cu)
 struct GemmProfile {
   bool enabled = false;
   std::vector<cudaEvent_t> ev;  // pairs
   std::vector<double> flops;
+  std::vector<int> kind;
 };
 static GemmProfile g_prof;
 
-static void prof_begin(cudaStream_t s, double flops) {
+bool prof_enabled() { return g_prof.enabled; }
+void prof_begin(cudaStream_t s, double flops, int kind = 0) {
   cudaEvent_t a, b;
   if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
   g_prof.ev.push_back(a);
   g_prof.ev.push_back(b);
   g_prof.flops.push_back(flops);
+  g_prof.kind.push_back(kind);
   cudaEventRecord(a, s);
 }
-static void prof_end(cudaStream_t s) { cudaEventRecord(g_prof.ev.back(), s); }
+void prof_end(cudaStream_t s) { cudaEventRecord(g_prof.ev.back(), s); }
+
+int gemm_nt_f64_emulated(int64_t, int64_t, int64_t, double, const double*, int64_t, const double*, int64_t, double, double*,
+                         int64_t, int32_t, cudaStream_t);  // gemm_oz.cu: 1 = done, 0 = not applicable, < 0 error
 
 int gemm_nt_f64(int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, int64_t a_bs,
                 const double* B, int64_t ldb, int64_t b_bs, double beta, double* C, int64_t ldc, int64_t c_bs,
@@ -571,6 +578,11 @@ int gemm_nt_f64(int64_t M, int64_t N, int64_t K, double alpha, const double* A, 
   int rc = check_gemm_args<double>(M, N, K, A, lda, B, ldb, C, ldc, batch);
   if (rc) return rc;
   if (M == 0 || N == 0) return 0;
+  if (batch == 1 && K >= 256) {  // large updates: int8-slice emulation on tcgen05 when the caller enabled it
+    rc = gemm_nt_f64_emulated(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, stream);
+    if (rc < 0) return rc;
+    if (rc == 1) return 0;
+  }
   const int32_t tiles_m = (int32_t)(M / GM_BM), tiles_n = (int32_t)(N / GM_BN);
   const int smem = 2 * GM_STAGES * GM_STAGE_ELEMS * (int)sizeof(double);
   const int n_groups = (tiles_m + 7) / 8;
@@ -704,22 +716,32 @@ void gpk_gemm_profile_enable(int32_t on) {
   for (cudaEvent_t e : gpk::g_prof.ev) cudaEventDestroy(e);
   gpk::g_prof.ev.clear();
   gpk::g_prof.flops.clear();
+  gpk::g_prof.kind.clear();
   gpk::g_prof.enabled = on != 0;
 }
-int gpk_gemm_profile_read(double* total_ms, double* total_flops, int64_t* launches) {
+static int profile_read_kind(int kind, double* total_ms, double* total_flops, int64_t* launches) {
   double ms = 0.0, fl = 0.0;
+  int64_t cnt = 0;
   const size_t n = gpk::g_prof.flops.size();
   for (size_t i = 0; i < n; ++i) {
+    if (kind >= 0 && gpk::g_prof.kind[i] != kind) continue;
     float t = 0.f;
     cudaError_t e = cudaEventElapsedTime(&t, gpk::g_prof.ev[2 * i], gpk::g_prof.ev[2 * i + 1]);
     if (e != cudaSuccess) return -1000 - (int)e;
     ms += t;
     fl += gpk::g_prof.flops[i];
+    ++cnt;
   }
   if (total_ms) *total_ms = ms;
   if (total_flops) *total_flops = fl;
-  if (launches) *launches = (int64_t)n;
+  if (launches) *launches = cnt;
   return 0;
+}
+int gpk_gemm_profile_read(double* total_ms, double* total_flops, int64_t* launches) {
+  return profile_read_kind(0, total_ms, total_flops, launches);
+}
+int gpk_gemm_profile_read_kind(int32_t kind, double* total_ms, double* total_flops, int64_t* launches) {
+  return profile_read_kind(kind, total_ms, total_flops, launches);
 }
 int gpk_gemm_nt_f64(int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, int64_t a_bstride,
                     const double* B, int64_t ldb, int64_t b_bstride, double beta, double* C, int64_t ldc,

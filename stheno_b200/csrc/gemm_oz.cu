@@ -26,6 +26,10 @@
 #include "common.cuh"
 
 namespace gpk {
+bool prof_enabled();  // gemm.cu: in-situ event profile (bench.py's roofline)
+void prof_begin(cudaStream_t, double flops, int kind);
+void prof_end(cudaStream_t);
+
 namespace {
 
 constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 64;  // BK in bytes = int8 elements
@@ -433,7 +437,10 @@ int oz_launch_gemm(int64_t M, int64_t N, int64_t K, double alpha, const int8_t* 
   tpc = tpc < 1 ? 1 : (tpc > 4 && force_tpc <= 0 ? 4 : tpc);
   OzParams p{alpha, C, scA + rowA, scB + rowB, ldc, (int32_t)rowA, (int32_t)rowB, (int32_t)(K / OZ_BK), lower,
              tiles_m, tiles_n, total, tpc, tri_rows, beta != 0.0 ? 1 : 0};
+  // profile: algorithmic (fp64-equivalent) flops of the tiles computed; the int8 work is S (S + 1) / 2 times that
+  if (prof_enabled()) prof_begin(stream, (double)total * 2.0 * OZ_BM * OZ_BN * (double)K, 1);
   oz_gemm_kernel<S><<<(unsigned)((total + tpc - 1) / tpc), OZ_THREADS, OzCfg<S>::SMEM_BYTES, stream>>>(mA, mB, mC, p);
+  if (prof_enabled()) prof_end(stream);
   GPK_COUNT_LAUNCH();
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -1000 - (int)e;
@@ -488,9 +495,58 @@ int oz_gemm_sliced(int64_t M, int64_t N, int64_t K, double alpha, const void* ws
   return GPK_ERR_ARG;
 }
 
+// ---- library-wide fp64 emulation mode (like cublasSetMathMode): set per host thread and device by the caller, who also
+// owns the scratch buffer.  Work that uses the scratch must be stream-ordered (one stream at a time per host thread). ----
+Emulation& emulation() {
+  static thread_local Emulation em[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return em[(dev < 0 || dev >= 64) ? 0 : dev];
+}
+
+static inline int64_t round_up_1k(int64_t x) { return (x + 1023) & ~int64_t(1023); }
+
+int64_t oz_gemm_scratch_bytes(int64_t M, int64_t N, int64_t K, int32_t S) {
+  return round_up_1k(oz_ws_bytes(M, K, S)) + oz_ws_bytes(N, K, S);
+}
+
+// 1 = done on the emulated path, 0 = not applicable (caller uses DMMA), < 0 = error
+int gemm_nt_f64_emulated(int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, const double* B,
+                         int64_t ldb, double beta, double* C, int64_t ldc, int32_t lower, cudaStream_t stream) {
+  const Emulation& em = emulation();
+  if (em.slices < 5 || em.slices > 8 || !em.scratch) return 0;
+  if (M % OZ_BM || N % OZ_BN || K % 128 || K > 65536 || lda % 2 || ldb % 2 || ldc % 2) return 0;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) % 16) return 0;
+  // worth it only when the product dwarfs the slicing passes and fills the machine
+  if (M < 256 || N < 256 || (double)M * (double)N * (double)K < 1.5e9) return 0;
+  const bool same = (A == B && lda == ldb && M >= N);
+  const int64_t off_b = same ? 0 : round_up_1k(oz_ws_bytes(M, K, em.slices));
+  if (em.bytes < off_b + oz_ws_bytes(same ? M : N, K, em.slices)) return 0;
+  int rc;
+  void* wsa = em.scratch;
+  void* wsb = static_cast<char*>(em.scratch) + off_b;
+  if ((rc = oz_slice_panel(A, lda, M, K, wsa, M, em.slices, stream))) return rc;
+  if (!same && (rc = oz_slice_panel(B, ldb, N, K, wsb, N, em.slices, stream))) return rc;
+  rc = oz_gemm_sliced(M, N, K, alpha, wsa, M, 0, same ? wsa : wsb, same ? M : N, 0, beta, C, ldc, lower, em.slices, stream);
+  return rc ? rc : 1;
+}
+
 }  // namespace gpk
 
 extern "C" {
+
+int gpk_set_f64_emulation(int32_t slices, void* scratch, int64_t scratch_bytes) {
+  if (slices != 0 && (slices < 5 || slices > 8)) return GPK_ERR_ARG;
+  if (slices != 0 && (!scratch || reinterpret_cast<uintptr_t>(scratch) % 1024 || scratch_bytes <= 0)) return GPK_ERR_ARG;
+  gpk::Emulation& em = gpk::emulation();
+  em.slices = slices;
+  em.scratch = slices ? scratch : nullptr;
+  em.bytes = slices ? scratch_bytes : 0;
+  return 0;
+}
+int64_t gpk_f64_emulation_scratch_bytes(int64_t M, int64_t N, int64_t K, int32_t slices) {
+  return gpk::oz_gemm_scratch_bytes(M, N, K, slices);
+}
 
 int64_t gpk_oz_ws_bytes(int64_t rows, int64_t K, int32_t slices) { return gpk::oz_ws_bytes(rows, K, slices); }
 

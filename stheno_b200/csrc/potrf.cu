@@ -450,6 +450,7 @@ int64_t oz_ws_bytes(int64_t rows, int64_t K, int32_t S);  // gemm_oz.cu
 int oz_slice_panel(const double*, int64_t, int64_t, int64_t, void*, int64_t, int32_t, cudaStream_t);
 int oz_gemm_sliced(int64_t, int64_t, int64_t, double, const void*, int64_t, int64_t, const void*, int64_t, int64_t, double,
                    double*, int64_t, int32_t, int32_t, cudaStream_t);
+// (Emulation / emulation(): common.cuh -- the caller's gpk_set_f64_emulation state for this host thread / device)
 
 // How the K = NB_OUTER trailing updates of an fp64 factorisation are formed:
 //   MODE_F64     fp64 tensor cores (DMMA) straight from the matrix
@@ -510,6 +511,16 @@ static int potrf_driver(T* A, int64_t lda, int64_t a_bs, int64_t n_pad, int64_t 
   if (n_pad % NB || extra_rows % NB || lda < n_pad) return GPK_ERR_ARG;
   if (lda % (16 / sizeof(T)) || reinterpret_cast<uintptr_t>(A) % 16) return GPK_ERR_ALIGN;
   const int64_t R = n_pad + extra_rows;
+  if (tr.mode == MODE_F64 && sizeof(T) == 8 && batch == 1 && n_pad >= 2048) {
+    // the caller enabled the int8-slice emulation (gpk_set_f64_emulation) and its scratch holds this panel's slices
+    const Emulation& em = emulation();
+    if (em.slices >= 5 && em.slices <= 8 && em.scratch && em.bytes >= oz_ws_bytes(R, NB_OUTER, em.slices)) {
+      tr.mode = MODE_OZAKI;
+      tr.ws = em.scratch;
+      tr.ws_bytes = em.bytes;
+      tr.slices = em.slices;
+    }
+  }
   tr.cap_rows = R;
   int rc;
   Lookahead& la = lookahead();

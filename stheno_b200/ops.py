@@ -176,6 +176,8 @@ def gemm_nt(A, Bm, C=None, *, alpha=1.0, beta=0.0, lower=False):
     for t in (A, Bm, C):
         if t.stride(2) != 1:
             raise ValueError("gemm_nt needs a unit inner stride")
+    if Bn == 1:
+        _emulation_for_gemm(A.device, A.dtype, M, N, K)
     rc = _fn("gpk_gemm_nt", A.dtype)(
         M, N, K, alpha, _ptr(A), A.stride(1), A.stride(0), _ptr(Bm), Bm.stride(1), Bm.stride(0), beta, _ptr(C),
         C.stride(1), C.stride(0), 1 if lower else 0, Bn, _stream(),
@@ -292,6 +294,9 @@ class Chol:
         if Bt.shape[2] != self.n_pad or Bt.shape[1] % TILE or Bt.stride(2) != 1:
             raise ValueError("solve_rows_ needs a padded [B, rows_pad, n_pad] buffer")
         Lp = self.L_padded()
+        if self.batch == 1:  # the recursive solve's largest GEMM: rows x n/2 x n/2
+            h = round_up(self.n_pad // 2)
+            _emulation_for_gemm(self.device, self.dtype, Bt.shape[1], self.n_pad - h + TILE, h)
         rc = _fn("gpk_trsm_right", self.dtype)(
             _ptr(Lp), Lp.stride(1), Lp.stride(0), self.n_pad, _ptr(Bt), Bt.stride(1), Bt.stride(0), Bt.shape[1],
             self.batch, _stream(),
@@ -351,24 +356,55 @@ def _potrf(W, n, n_pad, extra, k):
                                               B, _ptr(ws), ws.numel(), _stream())
         check(rc, "gpk_potrf_f64_tf32x3")
         return Chol(W, n, k, logdet, info)
-    slices = _oz_slices(getattr(_Bns, "precision", "fp64"))
-    if W.dtype == torch.float64 and B == 1 and slices and n_pad > 1024:
-        # fp64 emulated on the int8 tensor cores (error-free slicing, exact int32 products) for the trailing updates
-        lib = _lib.load()
-        ws = _aligned_bytes(lib.gpk_potrf_oz_ws_bytes(n_pad, extra, slices), W.device)
-        rc = lib.gpk_potrf_f64_oz(_ptr(W), W.stride(1), W.stride(0), n_pad, extra, _ptr(logdet), _ptr(info), B, slices,
-                                  _ptr(ws), ws.numel(), _stream())
-        check(rc, "gpk_potrf_f64_oz")
-        return Chol(W, n, k, logdet, info)
+    if W.dtype == torch.float64 and B == 1 and n_pad >= 2048:
+        slices = _oz_slices()
+        _set_emulation(W.device, slices, _lib.load().gpk_potrf_oz_ws_bytes(n_pad, extra, slices) if slices else 0)
     rc = _fn("gpk_potrf", W.dtype)(_ptr(W), W.stride(1), W.stride(0), n_pad, extra, _ptr(logdet), _ptr(info), B,
                                    _stream())
     check(rc, "gpk_potrf")
     return Chol(W, n, k, logdet, info)
 
 
-def _oz_slices(precision):
-    """``B.precision`` -> number of int8 slices of the emulated trailing update (0: not emulated)."""
-    return {"int8x6": 6, "int8x7": 7, "int8x8": 8, "int8x5": 5}.get(precision, 0)
+def _oz_slices():
+    """``B.precision`` -> number of int8 slices of the emulated large fp64 updates (0: native fp64 tensor cores only)."""
+    from . import B as _Bns
+
+    return {"auto": 7, "int8x5": 5, "int8x6": 6, "int8x7": 7, "int8x8": 8}.get(getattr(_Bns, "precision", "auto"), 0)
+
+
+#: per-device scratch handed to the library for the int8-slice emulation: [tensor, slices registered]
+_EMULATION = {}
+_EMULATION_MAX_BYTES = 8 << 30
+
+
+def _set_emulation(device, slices, need_bytes):
+    """Make the library's fp64 emulation mode on ``device`` match ``B.precision`` and own a scratch buffer of at least
+    ``need_bytes`` (grown on demand, capped: larger requests simply stay on the fp64 tensor cores)."""
+    key = torch.device(device).index or 0
+    buf, cur = _EMULATION.get(key, (None, 0))
+    lib = _lib.load()
+    if slices == 0:
+        if cur:
+            with torch.cuda.device(key):
+                check(lib.gpk_set_f64_emulation(0, None, 0), "gpk_set_f64_emulation")
+            _EMULATION[key] = (buf, 0)
+        return
+    need_bytes = min(int(need_bytes), _EMULATION_MAX_BYTES)
+    if buf is None or buf.numel() < need_bytes:
+        buf = _aligned_bytes(max(need_bytes, 64 << 20), torch.device("cuda", key))
+        cur = 0
+    if cur != slices:
+        with torch.cuda.device(key):
+            check(lib.gpk_set_f64_emulation(slices, _ptr(buf), buf.numel()), "gpk_set_f64_emulation")
+    _EMULATION[key] = (buf, slices)
+
+
+def _emulation_for_gemm(device, dtype, M, N, K):
+    if dtype != torch.float64:
+        return
+    slices = _oz_slices()
+    need = _lib.load().gpk_f64_emulation_scratch_bytes(M, N, K, slices) if slices and M * N * K >= 1.5e9 else 0
+    _set_emulation(device, slices, need)
 
 
 def _aligned_bytes(nbytes, device, align=1024):
@@ -434,11 +470,13 @@ def gemm_profile(enable):
     _lib.load().gpk_gemm_profile_enable(1 if enable else 0)
 
 
-def gemm_profile_read():
-    """``(total_ms, algorithmic_flops, launches)`` of the GEMM launches since ``gemm_profile(True)``; synchronises."""
+def gemm_profile_read(kind=0):
+    """``(total_ms, algorithmic_flops, launches)`` of the profiled GEMM launches since ``gemm_profile(True)``; synchronises.
+    ``kind``: 0 = fp64 DMMA trailing-update kernel, 1 = int8-slice emulation kernel (fp64-equivalent flops), -1 = both."""
     torch.cuda.synchronize()
     ms, fl, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
-    check(_lib.load().gpk_gemm_profile_read(ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n)), "gpk_gemm_profile_read")
+    check(_lib.load().gpk_gemm_profile_read_kind(int(kind), ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n)),
+          "gpk_gemm_profile_read_kind")
     return ms.value, fl.value, n.value
 
 

@@ -146,14 +146,17 @@ def test_opt_in_tf32x3_trailing_update(S):
     x = torch.as_tensor(rng.standard_normal((n, d)), device="cuda")
     y = torch.as_tensor(rng.standard_normal(n), device="cuda")
     f = S.GP(S.EQ().stretch(2.0))
-    ref = f(x, 0.1).logpdf(y)
+    before = S.B.precision
     try:
+        S.B.precision = "fp64"
+        ref = f(x, 0.1).logpdf(y)
         S.B.precision = "tf32x3"
         fast = f(x, 0.1).logpdf(y)
-    finally:
         S.B.precision = "fp64"
+        again = f(x, 0.1).logpdf(y)
+    finally:
+        S.B.precision = before
     rel = abs((fast - ref).item() / ref.item())
     assert rel < 1e-4, rel
     assert rel > 0  # it really took the other path
-    again = f(x, 0.1).logpdf(y)
     assert again.item() == ref.item()
