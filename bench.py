@@ -8,7 +8,10 @@ Synthetic inputs: x ~ N(0,1)^{n x d}, l = 2.0, s2 = 0.1, y ~ N(0,
 A "step" is one logpdf evaluation through the public API (``GP(k)(x, noise).logpdf(y)``).
   value  : steps/s with x, y already resident in HBM (CUDA-event timed, max over ranks)
   e2e    : the same call with HOST (pinned) x, y: H2D of the inputs and D2H of the scalar inside the timed region
-  roofline: in-situ event timing of the dominant kernel (fp64 tensor-core GEMM) vs the DMMA peak measured in-run
+  roofline: in-situ event timing of the dominant kernel -- by default the int8-slice emulation GEMM of the trailing updates
+            (tcgen05.mma.kind::i8) vs the int8 GEMM throughput measured in-run; with --precision fp64 the DMMA GEMM vs the
+            DMMA peak measured in-run
+  native_fp64: the same step with B.precision = "fp64" (all-DMMA), and the relative difference of the two log-pdfs
   cpu_baseline: the NumPy/SciPy oracle (the reference cannot be imported here) on the host cores, bounded sample
 N > 1 (torchrun): "replicas only" -- a single dense Cholesky does not shard; every rank evaluates its own
 independent problem (e.g. a hyper-parameter sweep), no data-path collective; value = N*K / max-rank time.
@@ -191,6 +194,48 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+ARITHMETIC = {
+    "auto": "fp64 storage and results; kernel build, leaf factorisations, panel solves, finish in native fp64 (FP64 pipe / DMMA); "
+            "the K=512 trailing updates emulated on the int8 tensor cores: operands split error-free into 7 signed 7-bit "
+            "slices (49 bits), exact int32 slice products (tcgen05.mma.kind::i8), fp64 recombination -- log-pdf agrees "
+            "with the all-DMMA path to ~1e-13 relative (see native_fp64.logpdf_rel_diff); parity bar 1e-10",
+    "fp64": "native fp64 everywhere (DMMA tensor cores for every GEMM-shaped update)",
+}
+ARITHMETIC["int8x7"] = ARITHMETIC["auto"]
+
+# one ncu --set full capture of the emulation kernel (profiles/r01_ncu_oz_gemm_details.csv): lower, M = N = 8192, K = 512
+OZ_TRAFFIC_SAMPLE = {"from": "profiles/r01_ncu_oz_gemm_details.csv (ncu --set full, one launch: lower, M=N=8192, K=512, 7 slices)",
+                     "dram_bytes": None, "algorithmic_bytes": 7 * 8192 * 512 + 2 * 8 * (8192 * 8192 // 2)}
+
+
+def int8_peak_tops(dev):
+    """Dense int8 tensor-core throughput measured in-run with the library GEMM (torch._int_mm -> cuBLASLt), the int8
+    counterpart of MEASURED_PEAKS.json's bf16 entry; falls back to 2 x that entry."""
+    import torch
+
+    try:
+        n = 8192
+        a = torch.randint(-100, 100, (n, n), device=dev, dtype=torch.int8)
+        b = torch.randint(-100, 100, (n, n), device=dev, dtype=torch.int8)
+        for _ in range(3):
+            torch._int_mm(a, b)
+        best = float("inf")
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch._int_mm(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12, "cuBLASLt int8 GEMM 8192^3 (torch._int_mm), best of 10, measured in-run"
+    except Exception as exc:  # pragma: no cover
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")) as fh:
+                return 2.0 * json.load(fh)["bf16_tflops"], f"2 x MEASURED_PEAKS.json bf16_tflops (torch._int_mm failed: {exc})"
+        except Exception:
+            return 4500.0, "nominal dense int8 peak (no measurement available)"
+
+
 def gpu_arm(args, rank, world, local_rank):
     import torch
 
@@ -207,6 +252,7 @@ def gpu_arm(args, rank, world, local_rank):
     from stheno_b200 import ops
 
     S.B.epsilon = 1e-12
+    S.B.precision = args.precision
     dev = torch.device("cuda", local_rank)
     x_np, y_np = make_inputs(2 + rank)
     x_dev = torch.as_tensor(x_np, device=dev)
@@ -266,30 +312,63 @@ def gpu_arm(args, rank, world, local_rank):
     value = world * args.steps / (ms * 1e-3)
     e2e_value = world * args.steps / (ms_e2e * 1e-3)
 
+    # the same step on the native fp64 tensor-core path (B.precision = "fp64"), for the record
+    native = None
+    if S.B.precision != "fp64":
+        chosen = S.B.precision
+        S.B.precision = "fp64"
+        for _ in range(2):
+            lp_native = step_resident()
+        ms_n, lp_native, _ = timed(step_resident, min(args.steps, 5))
+        S.B.precision = chosen
+        native = {"value": world * min(args.steps, 5) / (ms_n * 1e-3), "unit": UNIT, "ms_per_step": ms_n / min(args.steps, 5),
+                  "logpdf": float(lp_native), "logpdf_rel_diff": abs(float(lp) - float(lp_native)) / abs(float(lp_native)),
+                  "note": "B.precision='fp64': DMMA trailing updates (python bench.py --precision fp64 makes it the headline)"}
+
     if rank == 0:
-        # roofline leg: dominant kernel = fp64 tensor-core GEMM, timed in situ with events on its own stream
-        # (look-ahead off for these steps: with it on, GEMM launches share the SMs with the side-stream panel
-        # kernels and their event-bracketed durations overlap, which would not be a per-kernel figure)
+        # roofline leg: dominant kernel timed in situ with events on its own stream (look-ahead off for these steps: with
+        # it on, the update kernels share the SMs with the side-stream panel kernels and their event-bracketed durations
+        # overlap, which would not be a per-kernel figure)
         prof_steps = min(args.steps, 3)
         os.environ["GPK_NO_LOOKAHEAD"] = "1"
         ops.gemm_profile(True)
         for _ in range(prof_steps):
             step_resident()
-        g_ms, g_flops, g_launches = ops.gemm_profile_read()
+        d_ms, d_flops, d_launches = ops.gemm_profile_read(0)
+        o_ms, o_flops, o_launches = ops.gemm_profile_read(1)
         ops.gemm_profile(False)
         del os.environ["GPK_NO_LOOKAHEAD"]
-        peak = ops.probe_dmma_tflops()
-        achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else None
-        roofline = {
-            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": (achieved / peak) if achieved and peak > 0 else None, "traffic": None,
-            "kernel": "gpk::gemm_nt_f64_v3_kernel<32,2> (DMMA.8x8x4; the K>=512 trailing SYRK updates of the Cholesky)",
-            "peak_source": "fp64 DMMA issue peak measured in-run (gpk_probe_dmma_tflops); MEASURED_PEAKS.json has no fp64 entry",
-            "launches_per_step": g_launches / prof_steps, "kernel_ms_per_step": g_ms / prof_steps,
-            "traffic_sample": {"from": "profiles/r01_ncu_gemm_f64_v3_details.csv (ncu --set full, one launch: lower, M=N=8192, K=1024)",
-                               "dram_bytes": 727.4e6, "algorithmic_bytes": 604.0e6},
-            "whole_step_tflops": cost(N_FULL) / (ms / args.steps * 1e-3) / 1e12,
-        }
+        slices = ops._oz_slices()
+        if o_launches > 0:
+            # int8-slice emulation kernel: the work it does is S (S + 1) / 2 int8 GEMMs per fp64-equivalent GEMM
+            n_prod = slices * (slices + 1) // 2
+            peak, peak_src = int8_peak_tops(dev)
+            eq_tflops = o_flops / (o_ms * 1e-3) / 1e12
+            achieved = eq_tflops * n_prod
+            roofline = {
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)",
+                "frac": (achieved / peak) if peak else None, "traffic": None,
+                "kernel": f"gpk::oz_gemm_kernel<{slices}> (UTCIMMA = tcgen05.mma.kind::i8; the K=512 trailing SYRK updates of "
+                          f"the Cholesky as {n_prod} exact int8 slice products per fp64 product)",
+                "peak_source": peak_src,
+                "fp64_equivalent_tflops": eq_tflops, "int8_products_per_fp64_product": n_prod,
+                "launches_per_step": o_launches / prof_steps, "kernel_ms_per_step": o_ms / prof_steps,
+                "traffic_sample": OZ_TRAFFIC_SAMPLE,
+                "whole_step_tflops_fp64_equivalent": cost(N_FULL) / (ms / args.steps * 1e-3) / 1e12,
+            }
+        else:
+            peak = ops.probe_dmma_tflops()
+            achieved = d_flops / (d_ms * 1e-3) / 1e12 if d_ms > 0 else None
+            roofline = {
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": (achieved / peak) if achieved and peak > 0 else None, "traffic": None,
+                "kernel": "gpk::gemm_nt_f64_v3_kernel<32,2> (DMMA.8x8x4; the K>=512 trailing SYRK updates of the Cholesky)",
+                "peak_source": "fp64 DMMA issue peak measured in-run (gpk_probe_dmma_tflops); MEASURED_PEAKS.json has no fp64 entry",
+                "launches_per_step": d_launches / prof_steps, "kernel_ms_per_step": d_ms / prof_steps,
+                "traffic_sample": {"from": "profiles/r01_ncu_gemm_f64_v3_details.csv (ncu --set full, one launch: lower, M=N=8192, K=1024)",
+                                   "dram_bytes": 727.4e6, "algorithmic_bytes": 604.0e6},
+                "whole_step_tflops": cost(N_FULL) / (ms / args.steps * 1e-3) / 1e12,
+            }
         # bounded CPU baseline sample: the oracle at the largest n that fits ~25 s
         use_all_host_threads()
         n_s = pick_sample_n(25.0)
@@ -303,6 +382,8 @@ def gpu_arm(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
+            "arithmetic": ARITHMETIC.get(S.B.precision, S.B.precision), "precision_mode": S.B.precision,
+            "native_fp64": native,
             "config": {"workload": "EQ().stretch(2.0)+0.1*Delta(), n=16384, d=8, fp64: kernel build + Cholesky + logpdf",
                        "parallelism": "single GPU" if world == 1 else f"replicas only x{world} (independent problems, no data-path collective)",
                        "l2": "working set 2.1 GB per step >> 126 MB L2 (no flush needed)", "n": N_FULL, "d": D},
@@ -326,6 +407,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp64", "int8x6", "int8x7", "int8x8", "tf32x3"],
+                    help="stheno_b200.B.precision for the timed steps (auto = int8x7 emulation of the large fp64 updates)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
