@@ -393,15 +393,17 @@ static int64_t nb_outer() {
 // Side stream + events for the look-ahead (one set per process; the library is not re-entrant across host threads
 // for potrf, like the reference's global-state model -- SURVEY 8b "Ownership / threading").
 struct Lookahead {
-  cudaStream_t side = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaStream_t side = nullptr;  // the latency-bound chain: leaf factorisations + the rows the next leaf depends on
+  cudaStream_t bulk = nullptr;  // the rest of the panel rows (throughput work the chain does not wait for)
+  cudaEvent_t fork = nullptr, join = nullptr, leaf = nullptr, crit = nullptr, bulk_done = nullptr;
   bool ok = false;
   Lookahead() {
     int lo = 0, hi = 0;
     if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return;
     if (cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi) != cudaSuccess) return;
-    if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return;
-    if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) return;
+    if (cudaStreamCreateWithPriority(&bulk, cudaStreamNonBlocking, hi) != cudaSuccess) return;
+    for (cudaEvent_t* e : {&fork, &join, &leaf, &crit, &bulk_done})
+      if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return;
     ok = true;
   }
 };
@@ -436,6 +438,48 @@ static int factor_panel(T* A, int64_t lda, int64_t a_bs, int64_t R, int64_t kb, 
           return rc;
       }
     }
+  }
+  return 0;
+}
+
+// The same factorisation with the dependency chain cut short: the next leaf only depends on the rows INSIDE the panel's
+// diagonal block, so those ("critical" rows, <= NB_OUTER - 128 of them) are solved / updated on `chain` right behind the
+// leaf, while the rows below the diagonal block (all the throughput work) follow on the `bulk` stream, ordered by events.
+// On return `chain` has also waited for `bulk`.
+template <typename T>
+static int factor_panel_split(T* A, int64_t lda, int64_t a_bs, int64_t R, int64_t kb, int64_t ke, T* logdet, int32_t* info,
+                              int32_t batch, cudaStream_t chain, Lookahead& la) {
+  auto ce = [](cudaError_t e) { return e == cudaSuccess ? 0 : -1000 - (int)e; };
+  int rc;
+  const int64_t rest = R - ke;  // rows below the diagonal block
+  for (int64_t j = kb; j < ke; j += NB) {
+    T* Ajj = A + j * lda + j;
+    if ((rc = launch_potrf_leaf<T>(Ajj, lda, a_bs, logdet, info, (int32_t)j, batch, chain))) return rc;
+    const int64_t crit = ke - (j + NB);  // rows (and columns) of the diagonal block still to be factorised
+    T* A21 = A + (j + NB) * lda + j;     // critical rows of this block column
+    T* Arest = A + ke * lda + j;         // the rows below the diagonal block
+    if (rest > 0) {
+      if ((rc = ce(cudaEventRecord(la.leaf, chain)))) return rc;
+      if ((rc = ce(cudaStreamWaitEvent(la.bulk, la.leaf, 0)))) return rc;
+      if ((rc = trsm_leaf_fwd<T>(Ajj, lda, a_bs, Arest, lda, a_bs, rest, batch, la.bulk))) return rc;
+    }
+    if (crit > 0) {
+      if ((rc = trsm_leaf_fwd<T>(Ajj, lda, a_bs, A21, lda, a_bs, crit, batch, chain))) return rc;
+      if (rest > 0) {
+        if ((rc = ce(cudaEventRecord(la.crit, chain)))) return rc;
+        if ((rc = ce(cudaStreamWaitEvent(la.bulk, la.crit, 0)))) return rc;
+        if ((rc = gemm_nt(rest, crit, (int64_t)NB, T(-1), Arest, lda, a_bs, A21, lda, a_bs, T(1), A + ke * lda + (j + NB),
+                          lda, a_bs, 0, batch, la.bulk)))
+          return rc;
+      }
+      if ((rc = gemm_nt(crit, crit, (int64_t)NB, T(-1), A21, lda, a_bs, A21, lda, a_bs, T(1), A + (j + NB) * lda + (j + NB),
+                        lda, a_bs, 1, batch, chain)))
+        return rc;
+    }
+  }
+  if (rest > 0) {
+    if ((rc = ce(cudaEventRecord(la.bulk_done, la.bulk)))) return rc;
+    if ((rc = ce(cudaStreamWaitEvent(chain, la.bulk_done, 0)))) return rc;
   }
   return 0;
 }
@@ -488,20 +532,23 @@ int prepare_panel<double>(const Trailing& t, const double* P, int64_t ldp, int64
   return 0;
 }
 
-// trailing update C[M x N] (lower tiles) -= P[r0 : r0 + M] P[r0 : r0 + N]^T; `r0` = first row of the update relative to
-// the first row of the prepared panel copy.
+// trailing update C[M x N] -= P[rA : rA + M] P[rB : rB + N]^T (lower: only the tiles that touch the lower triangle);
+// rA / rB = first row of the operands relative to the first row of the prepared panel copy, PA / PB the same rows in
+// the matrix itself.
 template <typename T>
-static int trailing_update(int used, const Trailing&, int64_t r0, int64_t M, int64_t N, int64_t K, const T* P, int64_t lda,
-                           int64_t a_bs, T* C, int32_t batch, cudaStream_t stream) {
-  return gemm_nt(M, N, K, T(-1), P, lda, a_bs, P, lda, a_bs, T(1), C, lda, a_bs, 1, batch, stream);
+static int trailing_update(int used, const Trailing&, int64_t rA, int64_t rB, int64_t M, int64_t N, int64_t K, const T* PA,
+                           const T* PB, int64_t lda, int64_t a_bs, T* C, int32_t lower, int32_t batch, cudaStream_t stream) {
+  return gemm_nt(M, N, K, T(-1), PA, lda, a_bs, PB, lda, a_bs, T(1), C, lda, a_bs, lower, batch, stream);
 }
 template <>
-int trailing_update<double>(int used, const Trailing& t, int64_t r0, int64_t M, int64_t N, int64_t K, const double* P,
-                            int64_t lda, int64_t a_bs, double* C, int32_t batch, cudaStream_t stream) {
-  if (used == MODE_TF32X3) return syrk_f64_tf32x3(M, N, K, static_cast<const float*>(t.ws) + r0 * K, C, lda, stream);
+int trailing_update<double>(int used, const Trailing& t, int64_t rA, int64_t rB, int64_t M, int64_t N, int64_t K,
+                            const double* PA, const double* PB, int64_t lda, int64_t a_bs, double* C, int32_t lower,
+                            int32_t batch, cudaStream_t stream) {
+  if (used == MODE_TF32X3 && rA == rB && lower)
+    return syrk_f64_tf32x3(M, N, K, static_cast<const float*>(t.ws) + rA * K, C, lda, stream);
   if (used == MODE_OZAKI)
-    return oz_gemm_sliced(M, N, K, -1.0, t.ws, t.cap_rows, r0, t.ws, t.cap_rows, r0, 1.0, C, lda, 1, t.slices, stream);
-  return gemm_nt(M, N, K, -1.0, P, lda, a_bs, P, lda, a_bs, 1.0, C, lda, a_bs, 1, batch, stream);
+    return oz_gemm_sliced(M, N, K, -1.0, t.ws, t.cap_rows, rA, t.ws, t.cap_rows, rB, 1.0, C, lda, lower, t.slices, stream);
+  return gemm_nt(M, N, K, -1.0, PA, lda, a_bs, PB, lda, a_bs, 1.0, C, lda, a_bs, lower, batch, stream);
 }
 
 template <typename T>
@@ -522,9 +569,18 @@ static int potrf_driver(T* A, int64_t lda, int64_t a_bs, int64_t n_pad, int64_t 
     }
   }
   tr.cap_rows = R;
+  // Inside the factorisation the scratch belongs to the panel slices, and updates are enqueued on several streams at once:
+  // the generic GEMM entry must not pick the emulated path (and the scratch) on its own while this driver enqueues work.
+  struct SuspendEmulation {
+    Emulation& em;
+    int32_t saved;
+    explicit SuspendEmulation(Emulation& e) : em(e), saved(e.slices) { em.slices = 0; }
+    ~SuspendEmulation() { em.slices = saved; }
+  } suspend(emulation());
   int rc;
   Lookahead& la = lookahead();
   const bool use_la = la.ok && n_pad > 2 * NB_OUTER && getenv("GPK_NO_LOOKAHEAD") == nullptr;
+  const bool split = use_la && getenv("GPK_NO_SPLIT") == nullptr;
   auto ce = [](cudaError_t e) { return e == cudaSuccess ? 0 : -1000 - (int)e; };
 
   const int64_t ke0 = NB_OUTER < n_pad ? NB_OUTER : n_pad;
@@ -538,26 +594,41 @@ static int potrf_driver(T* A, int64_t lda, int64_t a_bs, int64_t n_pad, int64_t 
     int used = MODE_F64;
     if ((rc = prepare_panel<T>(tr, P, lda, R - ke, K, batch, stream, &used))) return rc;
     const bool more = ke2 < n_pad;
+    const int64_t W = ke2 - ke;  // width of the next panel
+    T* Ckk = A + ke * lda + ke;  // top-left corner of the trailing matrix
+    const T* P2 = A + ke2 * lda + kb;
     if (use_la && more) {
-      // side stream (high priority): (a) the next panel's columns, then that panel's factorisation;
+      // side streams (high priority): (a) the next panel's columns, then that panel's factorisation;
       // caller's stream: (b) everything to the right of it.  (a) and (b) are independent (both only read panel i), so
       // they run concurrently and the short (a) no longer costs a kernel tail of its own.
       if ((rc = ce(cudaEventRecord(la.fork, stream)))) return rc;
       if ((rc = ce(cudaStreamWaitEvent(la.side, la.fork, 0)))) return rc;
-      if ((rc = trailing_update<T>(used, tr, 0, R - ke, ke2 - ke, K, P, lda, a_bs, A + ke * lda + ke, batch, la.side)))
-        return rc;
-      if ((rc = factor_panel<T>(A, lda, a_bs, R, ke, ke2, logdet, info, batch, la.side))) return rc;
+      if (split && used != MODE_TF32X3) {
+        // (a) in two parts: the next panel's diagonal block first (the chain starts on it at once), the rows below on `bulk`
+        if ((rc = ce(cudaStreamWaitEvent(la.bulk, la.fork, 0)))) return rc;
+        if ((rc = trailing_update<T>(used, tr, 0, 0, W, W, K, P, P, lda, a_bs, Ckk, 1, batch, la.side))) return rc;
+        if (R - ke2 > 0 && (rc = trailing_update<T>(used, tr, W, 0, R - ke2, W, K, P2, P, lda, a_bs, A + ke2 * lda + ke, 0,
+                                                    batch, la.bulk)))
+          return rc;
+      } else {
+        if ((rc = trailing_update<T>(used, tr, 0, 0, R - ke, W, K, P, P, lda, a_bs, Ckk, 1, batch, la.side))) return rc;
+        if (split && (rc = ce(cudaStreamWaitEvent(la.bulk, la.fork, 0)))) return rc;
+      }
+      if (split) {
+        if ((rc = factor_panel_split<T>(A, lda, a_bs, R, ke, ke2, logdet, info, batch, la.side, la))) return rc;
+      } else {
+        if ((rc = factor_panel<T>(A, lda, a_bs, R, ke, ke2, logdet, info, batch, la.side))) return rc;
+      }
       if ((rc = ce(cudaEventRecord(la.join, la.side)))) return rc;
-      if ((rc = trailing_update<T>(used, tr, ke2 - ke, R - ke2, n_pad - ke2, K, A + ke2 * lda + kb, lda, a_bs,
-                                   A + ke2 * lda + ke2, batch, stream)))
+      if ((rc = trailing_update<T>(used, tr, W, W, R - ke2, n_pad - ke2, K, P2, P2, lda, a_bs, A + ke2 * lda + ke2, 1, batch,
+                                   stream)))
         return rc;
       if ((rc = ce(cudaStreamWaitEvent(stream, la.join, 0)))) return rc;
     } else {
-      if ((rc = trailing_update<T>(used, tr, 0, R - ke, ke2 - ke, K, P, lda, a_bs, A + ke * lda + ke, batch, stream)))
-        return rc;
+      if ((rc = trailing_update<T>(used, tr, 0, 0, R - ke, W, K, P, P, lda, a_bs, Ckk, 1, batch, stream))) return rc;
       if (more) {
-        if ((rc = trailing_update<T>(used, tr, ke2 - ke, R - ke2, n_pad - ke2, K, A + ke2 * lda + kb, lda, a_bs,
-                                     A + ke2 * lda + ke2, batch, stream)))
+        if ((rc = trailing_update<T>(used, tr, W, W, R - ke2, n_pad - ke2, K, P2, P2, lda, a_bs, A + ke2 * lda + ke2, 1,
+                                     batch, stream)))
           return rc;
       }
       if ((rc = factor_panel<T>(A, lda, a_bs, R, ke, ke2, logdet, info, batch, stream))) return rc;
