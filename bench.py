@@ -205,7 +205,7 @@ ARITHMETIC["int8x7"] = ARITHMETIC["auto"]
 
 # one ncu --set full capture of the emulation kernel (profiles/r01_ncu_oz_gemm_details.csv): lower, M = N = 8192, K = 512
 OZ_TRAFFIC_SAMPLE = {"from": "profiles/r01_ncu_oz_gemm_details.csv (ncu --set full, one launch: lower, M=N=8192, K=512, 7 slices)",
-                     "dram_bytes": None, "algorithmic_bytes": 7 * 8192 * 512 + 2 * 8 * (8192 * 8192 // 2)}
+                     "dram_bytes": 520.2e6, "algorithmic_bytes": 7 * 8192 * 512 + 2 * 8 * (8192 * 8192 // 2)}
 
 
 def int8_peak_tops(dev):
