@@ -225,9 +225,14 @@ __device__ __forceinline__ int frag_index(int n, int k) {
 
 // T = storage type (double or float).  The arithmetic is always fp64 on the DMMA pipe: for fp32 problems the leaf TRSM is
 // < 2 % of the flops, and doing it in fp64 costs nothing while removing one source of fp32 round-off.
+// With D != nullptr (one CTA per matrix: the 128 rows right below L11) the kernel goes on to the rank-128 update of the
+// next diagonal block, D -= X X^T (lower 8 x 8 blocks), without leaving the SM: the solved rows are still in registers as
+// A-operand fragments and are parked in shared memory (over L11, fragment-major) as the B operand.  That is the whole
+// dependency of the next leaf factorisation in ONE launch (leaf -> this kernel -> next leaf).
 template <typename T>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-trsm_leaf_tc_kernel(const T* __restrict__ L, int64_t ldl, int64_t l_bs, T* __restrict__ B, int64_t ldb, int64_t b_bs) {
+trsm_leaf_tc_kernel(const T* __restrict__ L, int64_t ldl, int64_t l_bs, T* __restrict__ B, int64_t ldb, int64_t b_bs,
+                    T* __restrict__ D, int64_t ldd, int64_t d_bs) {
   extern __shared__ __align__(16) unsigned char tc_smem[];
   double* Ls = reinterpret_cast<double*>(tc_smem);  // 128 x 128 fragment-major
   double* Ld = Ls + NB * NB;                         // [8][16][17] diagonal blocks (natural layout)
@@ -320,6 +325,35 @@ trsm_leaf_tc_kernel(const T* __restrict__ L, int64_t ldl, int64_t l_bs, T* __res
     Bw[cb * 8] = (T)acc[cb][0];
     Bw[cb * 8 + 1] = (T)acc[cb][1];
   }
+  if (D == nullptr) return;
+
+  // ---- fused rank-128 update of the next diagonal block: D[8w .. 8w+7, 8cb .. 8cb+7] -= X_w X_cb^T for cb <= w ----
+  __syncthreads();  // every warp is done reading L11 from shared memory
+#pragma unroll
+  for (int cb = 0; cb < 16; ++cb)  // fragment (row block = warp, k8 group = cb): lane's double2 at ((w*16+cb)*32+lane)*2
+    *reinterpret_cast<double2*>(Ls + ((warp * 16 + cb) * 32 + lane) * 2) = make_double2(acc[cb][0], acc[cb][1]);
+  __syncthreads();
+  D += (int64_t)blockIdx.y * d_bs;
+  T* Dw = D + (int64_t)(warp * 8 + (lane >> 2)) * ldd + 2 * (lane & 3);
+  // warp w owns w + 1 output blocks: pair the work as (w, 15 - w) would need a second pass; instead split every block's
+  // k range in halves across the two DMMA chains below (independent accumulators), which keeps the pipe full
+#pragma unroll 1
+  for (int cb = 0; cb <= warp; ++cb) {
+    double d0[2] = {0.0, 0.0}, d1[2] = {0.0, 0.0};
+    const double c0 = (double)Dw[cb * 8], c1 = (double)Dw[cb * 8 + 1];
+    const double* Xb = Lf + (cb * 16) * 64;
+#pragma unroll
+    for (int kg = 0; kg < 8; ++kg) {
+      const double2 b0 = *reinterpret_cast<const double2*>(Xb + kg * 64);
+      const double2 b1 = *reinterpret_cast<const double2*>(Xb + (kg + 8) * 64);
+      dmma884(d0[0], d0[1], acc[kg][0], b0.x);
+      dmma884(d1[0], d1[1], acc[kg + 8][0], b1.x);
+      dmma884(d0[0], d0[1], acc[kg][1], b0.y);
+      dmma884(d1[0], d1[1], acc[kg + 8][1], b1.y);
+    }
+    Dw[cb * 8] = (T)(c0 - (d0[0] + d1[0]));
+    Dw[cb * 8 + 1] = (T)(c1 - (d0[1] + d1[1]));
+  }
 }
 
 template <typename T>
@@ -334,7 +368,25 @@ static int launch_trsm_leaf_tc(const T* L, int64_t ldl, int64_t l_bs, T* B, int6
     attr_set = true;
   }
   dim3 grid((unsigned)(rows / TC_ROWS), (unsigned)batch);
-  trsm_leaf_tc_kernel<T><<<grid, TC_THREADS, smem, stream>>>(L, ldl, l_bs, B, ldb, b_bs);
+  trsm_leaf_tc_kernel<T><<<grid, TC_THREADS, smem, stream>>>(L, ldl, l_bs, B, ldb, b_bs, nullptr, 0, 0);
+  GPK_COUNT_LAUNCH();
+  GPK_CHECK_LAUNCH();
+  return 0;
+}
+
+// the 128 rows below L11 solved AND the next diagonal block updated, one CTA per matrix (see the kernel)
+template <typename T>
+static int launch_diag_step(const T* L, int64_t ldl, int64_t l_bs, T* B, int64_t ldb, int64_t b_bs, T* D, int64_t ldd,
+                            int64_t d_bs, int32_t batch, cudaStream_t stream) {
+  const int smem = (NB * NB + 8 * 16 * 17) * (int)sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(trsm_leaf_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return -1000 - (int)e;
+    attr_set = true;
+  }
+  dim3 grid(1, (unsigned)batch);
+  trsm_leaf_tc_kernel<T><<<grid, TC_THREADS, smem, stream>>>(L, ldl, l_bs, B, ldb, b_bs, D, ldd, d_bs);
   GPK_COUNT_LAUNCH();
   GPK_CHECK_LAUNCH();
   return 0;
@@ -442,42 +494,50 @@ static int factor_panel(T* A, int64_t lda, int64_t a_bs, int64_t R, int64_t kb, 
   return 0;
 }
 
-// The same factorisation with the dependency chain cut short: the next leaf only depends on the rows INSIDE the panel's
-// diagonal block, so those ("critical" rows, <= NB_OUTER - 128 of them) are solved / updated on `chain` right behind the
-// leaf, while the rows below the diagonal block (all the throughput work) follow on the `bulk` stream, ordered by events.
+// The same factorisation with the dependency chain cut short.  The next leaf only depends on the next 128 x 128 diagonal
+// block, so `chain` runs  leaf -> diag_step (solve the 128 rows below the leaf AND update the next diagonal block, one
+// launch) -> leaf -> ...  while every other row of the block column (the rest of the panel's diagonal block and all the
+// rows below it: the throughput work) is solved / updated on the `bulk` stream, ordered by events:
+//   bulk(j)  waits for leaf(j) (solve) and diag_step(j) (its rows are the B operand of the update);
+//   diag_step(j + 128) waits for bulk(j) (which updated the rows it solves).
 // On return `chain` has also waited for `bulk`.
 template <typename T>
 static int factor_panel_split(T* A, int64_t lda, int64_t a_bs, int64_t R, int64_t kb, int64_t ke, T* logdet, int32_t* info,
                               int32_t batch, cudaStream_t chain, Lookahead& la) {
   auto ce = [](cudaError_t e) { return e == cudaSuccess ? 0 : -1000 - (int)e; };
   int rc;
-  const int64_t rest = R - ke;  // rows below the diagonal block
+  bool bulk_pending = false;  // bulk work the next diag_step has to wait for
   for (int64_t j = kb; j < ke; j += NB) {
     T* Ajj = A + j * lda + j;
     if ((rc = launch_potrf_leaf<T>(Ajj, lda, a_bs, logdet, info, (int32_t)j, batch, chain))) return rc;
-    const int64_t crit = ke - (j + NB);  // rows (and columns) of the diagonal block still to be factorised
-    T* A21 = A + (j + NB) * lda + j;     // critical rows of this block column
-    T* Arest = A + ke * lda + j;         // the rows below the diagonal block
-    if (rest > 0) {
+    const int64_t j1 = j + NB;           // next diagonal block
+    const bool has_next = j1 < ke;       // ... inside this panel
+    const int64_t b0 = has_next ? j1 + NB : j1;  // first row the bulk stream handles
+    const int64_t brows = R - b0;
+    if (brows > 0) {
       if ((rc = ce(cudaEventRecord(la.leaf, chain)))) return rc;
       if ((rc = ce(cudaStreamWaitEvent(la.bulk, la.leaf, 0)))) return rc;
-      if ((rc = trsm_leaf_fwd<T>(Ajj, lda, a_bs, Arest, lda, a_bs, rest, batch, la.bulk))) return rc;
+      if ((rc = trsm_leaf_fwd<T>(Ajj, lda, a_bs, A + b0 * lda + j, lda, a_bs, brows, batch, la.bulk))) return rc;
     }
-    if (crit > 0) {
-      if ((rc = trsm_leaf_fwd<T>(Ajj, lda, a_bs, A21, lda, a_bs, crit, batch, chain))) return rc;
-      if (rest > 0) {
+    if (has_next) {
+      if (bulk_pending) {  // the rows this step solves were updated by the previous step's bulk GEMM
+        if ((rc = ce(cudaStreamWaitEvent(chain, la.bulk_done, 0)))) return rc;
+      }
+      T* X1 = A + j1 * lda + j;  // rows [j1, j1 + 128) of this block column
+      if ((rc = launch_diag_step<T>(Ajj, lda, a_bs, X1, lda, a_bs, A + j1 * lda + j1, lda, a_bs, batch, chain))) return rc;
+      if (brows > 0) {
         if ((rc = ce(cudaEventRecord(la.crit, chain)))) return rc;
         if ((rc = ce(cudaStreamWaitEvent(la.bulk, la.crit, 0)))) return rc;
-        if ((rc = gemm_nt(rest, crit, (int64_t)NB, T(-1), Arest, lda, a_bs, A21, lda, a_bs, T(1), A + ke * lda + (j + NB),
-                          lda, a_bs, 0, batch, la.bulk)))
+        // rows [b0, R) x columns [j1, ke) of the panel -= X[b0:, j] X[j1:ke, j]^T
+        if ((rc = gemm_nt(brows, ke - j1, (int64_t)NB, T(-1), A + b0 * lda + j, lda, a_bs, X1, lda, a_bs, T(1),
+                          A + b0 * lda + j1, lda, a_bs, 0, batch, la.bulk)))
           return rc;
+        if ((rc = ce(cudaEventRecord(la.bulk_done, la.bulk)))) return rc;
+        bulk_pending = true;
       }
-      if ((rc = gemm_nt(crit, crit, (int64_t)NB, T(-1), A21, lda, a_bs, A21, lda, a_bs, T(1), A + (j + NB) * lda + (j + NB),
-                        lda, a_bs, 1, batch, chain)))
-        return rc;
     }
   }
-  if (rest > 0) {
+  if (R - ke > 0 || bulk_pending) {
     if ((rc = ce(cudaEventRecord(la.bulk_done, la.bulk)))) return rc;
     if ((rc = ce(cudaStreamWaitEvent(chain, la.bulk_done, 0)))) return rc;
   }
