@@ -232,24 +232,29 @@ __device__ __forceinline__ int frag_index(int n, int k) {
 template <typename T>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 trsm_leaf_tc_kernel(const T* __restrict__ L, int64_t ldl, int64_t l_bs, T* __restrict__ B, int64_t ldb, int64_t b_bs,
-                    T* __restrict__ D, int64_t ldd, int64_t d_bs) {
+                    T* __restrict__ D, int64_t ldd, int64_t d_bs, int32_t rows_per_cta) {
   extern __shared__ __align__(16) unsigned char tc_smem[];
   double* Ls = reinterpret_cast<double*>(tc_smem);  // 128 x 128 fragment-major
   double* Ld = Ls + NB * NB;                         // [8][16][17] diagonal blocks (natural layout)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   L += (int64_t)blockIdx.y * l_bs;
-  B += (int64_t)blockIdx.y * b_bs + (int64_t)blockIdx.x * TC_ROWS * ldb;
+  B += (int64_t)blockIdx.y * b_bs + (int64_t)blockIdx.x * rows_per_cta * ldb;
 
   // (1) L11 (lower part, zeros above) -> fragment-major shared memory; 8192 granules of 2 doubles
-#pragma unroll 4
-  for (int gi = tid; gi < NB * NB / 2; gi += TC_THREADS) {
+#pragma unroll
+  for (int gi = tid; gi < NB * NB / 2; gi += TC_THREADS) {  // 16 independent 2-element loads in flight per thread
     const int c = gi >> 6, g = gi & 63;  // row c, granule g: columns 2g, 2g+1
     const int k = 2 * g;
     double2 v = make_double2(0.0, 0.0);
     if (k <= c) {
-      const T* src = L + (int64_t)c * ldl + k;
-      v.x = (double)src[0];
-      v.y = (k + 1 > c) ? 0.0 : (double)src[1];
+      const T* src = L + (int64_t)c * ldl + k;  // (k even, ldl even, L 16-byte aligned: one vector load)
+      if (sizeof(T) == 8) {
+        v = *reinterpret_cast<const double2*>(src);
+      } else {
+        const float2 f = *reinterpret_cast<const float2*>(src);
+        v = make_double2((double)f.x, (double)f.y);
+      }
+      if (k + 1 > c) v.y = 0.0;
     }
     *reinterpret_cast<double2*>(Ls + frag_index(c, k)) = v;
     if ((c >> 4) == (k >> 4)) {  // diagonal 16 x 16 block: natural copy for the inversion
@@ -281,7 +286,10 @@ trsm_leaf_tc_kernel(const T* __restrict__ L, int64_t ldl, int64_t l_bs, T* __res
   }
   __syncthreads();
 
-  // (3) this warp's 8 rows as sixteen accumulator fragments
+  // (3) this warp's 8 rows as sixteen accumulator fragments.  (With rows_per_cta < 128 -- the latency-critical launches of
+  //     the factorisation chain spread 128 rows over 4 CTAs -- only the first rows_per_cta / 8 warps have rows: the solve
+  //     is bound by the DMMA rate of ONE SM, 11 us for 128 rows.)
+  if (warp * 8 >= rows_per_cta) return;
   double acc[16][2];
   T* Bw = B + (int64_t)(warp * 8 + (lane >> 2)) * ldb + 2 * (lane & 3);
 #pragma unroll
@@ -368,13 +376,52 @@ static int launch_trsm_leaf_tc(const T* L, int64_t ldl, int64_t l_bs, T* B, int6
     attr_set = true;
   }
   dim3 grid((unsigned)(rows / TC_ROWS), (unsigned)batch);
-  trsm_leaf_tc_kernel<T><<<grid, TC_THREADS, smem, stream>>>(L, ldl, l_bs, B, ldb, b_bs, nullptr, 0, 0);
+  trsm_leaf_tc_kernel<T><<<grid, TC_THREADS, smem, stream>>>(L, ldl, l_bs, B, ldb, b_bs, nullptr, 0, 0, TC_ROWS);
   GPK_COUNT_LAUNCH();
   GPK_CHECK_LAUNCH();
   return 0;
 }
 
-// the 128 rows below L11 solved AND the next diagonal block updated, one CTA per matrix (see the kernel)
+// ---- rank-128 update of one 128 x 128 diagonal block, D -= X X^T (lower 8 x 8 blocks), spread over 17 CTAs: one warp per
+// 8 x 8 output block, both operands read straight from X in global memory (L2) in DMMA fragment order.  Latency-critical:
+// it sits between two leaf factorisations on the chain, where a single-SM tile update would cost ~12 us.
+template <typename T>
+__global__ void __launch_bounds__(256)
+diag_syrk_kernel(const T* __restrict__ X, int64_t ldx, int64_t x_bs, T* __restrict__ D, int64_t ldd, int64_t d_bs) {
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * 8 + (threadIdx.x >> 5);  // 0 .. 135: lower-triangular block index
+  int rb = (int)((sqrtf(8.f * (float)g + 1.f) - 1.f) * 0.5f);
+  while (rb * (rb + 1) / 2 > g) --rb;
+  while ((rb + 1) * (rb + 2) / 2 <= g) ++rb;
+  const int cb = g - rb * (rb + 1) / 2;
+  X += (int64_t)blockIdx.y * x_bs;
+  D += (int64_t)blockIdx.y * d_bs;
+  const T* Xa = X + (int64_t)(rb * 8 + (lane >> 2)) * ldx + 2 * (lane & 3);
+  const T* Xb = X + (int64_t)(cb * 8 + (lane >> 2)) * ldx + 2 * (lane & 3);
+  double a[16][2], b[16][2];
+#pragma unroll
+  for (int kg = 0; kg < 16; ++kg) {
+    a[kg][0] = (double)Xa[kg * 8];
+    a[kg][1] = (double)Xa[kg * 8 + 1];
+    b[kg][0] = (double)Xb[kg * 8];
+    b[kg][1] = (double)Xb[kg * 8 + 1];
+  }
+  T* Dp = D + (int64_t)(rb * 8 + (lane >> 2)) * ldd + cb * 8 + 2 * (lane & 3);
+  const double c0 = (double)Dp[0], c1 = (double)Dp[1];
+  double d0[2] = {0.0, 0.0}, d1[2] = {0.0, 0.0};
+#pragma unroll
+  for (int kg = 0; kg < 8; ++kg) {  // two independent DMMA chains
+    dmma884(d0[0], d0[1], a[kg][0], b[kg][0]);
+    dmma884(d1[0], d1[1], a[kg + 8][0], b[kg + 8][0]);
+    dmma884(d0[0], d0[1], a[kg][1], b[kg][1]);
+    dmma884(d1[0], d1[1], a[kg + 8][1], b[kg + 8][1]);
+  }
+  Dp[0] = (T)(c0 - (d0[0] + d1[0]));
+  Dp[1] = (T)(c1 - (d0[1] + d1[1]));
+}
+
+// The dependency of the next leaf in two short launches: the 128 rows below L11 solved by 4 CTAs (32 rows each), then the
+// next diagonal block updated by 17 CTAs.
 template <typename T>
 static int launch_diag_step(const T* L, int64_t ldl, int64_t l_bs, T* B, int64_t ldb, int64_t b_bs, T* D, int64_t ldd,
                             int64_t d_bs, int32_t batch, cudaStream_t stream) {
@@ -385,8 +432,19 @@ static int launch_diag_step(const T* L, int64_t ldl, int64_t l_bs, T* B, int64_t
     if (e != cudaSuccess) return -1000 - (int)e;
     attr_set = true;
   }
-  dim3 grid(1, (unsigned)batch);
-  trsm_leaf_tc_kernel<T><<<grid, TC_THREADS, smem, stream>>>(L, ldl, l_bs, B, ldb, b_bs, D, ldd, d_bs);
+  static const bool fused = getenv("GPK_DIAG_FUSED") != nullptr;  // one-CTA variant (solve + update in one launch)
+  if (fused) {
+    trsm_leaf_tc_kernel<T><<<dim3(1, (unsigned)batch), TC_THREADS, smem, stream>>>(L, ldl, l_bs, B, ldb, b_bs, D, ldd, d_bs,
+                                                                                  TC_ROWS);
+    GPK_COUNT_LAUNCH();
+    GPK_CHECK_LAUNCH();
+    return 0;
+  }
+  trsm_leaf_tc_kernel<T><<<dim3(4, (unsigned)batch), TC_THREADS, smem, stream>>>(L, ldl, l_bs, B, ldb, b_bs, nullptr, 0, 0,
+                                                                                32);
+  GPK_COUNT_LAUNCH();
+  GPK_CHECK_LAUNCH();
+  diag_syrk_kernel<T><<<dim3(17, (unsigned)batch), 256, 0, stream>>>(B, ldb, b_bs, D, ldd, d_bs);
   GPK_COUNT_LAUNCH();
   GPK_CHECK_LAUNCH();
   return 0;
