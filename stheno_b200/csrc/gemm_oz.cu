@@ -515,20 +515,30 @@ int gemm_nt_f64_emulated(int64_t M, int64_t N, int64_t K, double alpha, const do
                          int64_t ldb, double beta, double* C, int64_t ldc, int32_t lower, cudaStream_t stream) {
   const Emulation& em = emulation();
   if (em.slices < 5 || em.slices > 8 || !em.scratch) return 0;
-  if (M % OZ_BM || N % OZ_BN || K % 128 || K > 65536 || lda % 2 || ldb % 2 || ldc % 2) return 0;
+  if (M % OZ_BM || N % OZ_BN || K % 128 || lda % 2 || ldb % 2 || ldc % 2) return 0;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) % 16) return 0;
   // worth it only when the product dwarfs the slicing passes and fills the machine
   if (M < 256 || N < 256 || (double)M * (double)N * (double)K < 1.5e9) return 0;
   const bool same = (A == B && lda == ldb && M >= N);
-  const int64_t off_b = same ? 0 : round_up_1k(oz_ws_bytes(M, K, em.slices));
-  if (em.bytes < off_b + oz_ws_bytes(same ? M : N, K, em.slices)) return 0;
+  // int32 accumulation is exact for K <= 65536 per pass: longer reductions (the sparse path's n = 262144) run as several
+  // passes over K chunks, each adding into C
+  constexpr int64_t KC_MAX = 65536;
+  const int64_t passes = (K + KC_MAX - 1) / KC_MAX;
+  const int64_t kc = ((K / passes + 127) / 128) * 128;  // chunk length (multiple of 128), last chunk = remainder
+  const int64_t off_b = same ? 0 : round_up_1k(oz_ws_bytes(M, kc, em.slices));
+  if (em.bytes < off_b + oz_ws_bytes(same ? M : N, kc, em.slices)) return 0;
   int rc;
   void* wsa = em.scratch;
   void* wsb = static_cast<char*>(em.scratch) + off_b;
-  if ((rc = oz_slice_panel(A, lda, M, K, wsa, M, em.slices, stream))) return rc;
-  if (!same && (rc = oz_slice_panel(B, ldb, N, K, wsb, N, em.slices, stream))) return rc;
-  rc = oz_gemm_sliced(M, N, K, alpha, wsa, M, 0, same ? wsa : wsb, same ? M : N, 0, beta, C, ldc, lower, em.slices, stream);
-  return rc ? rc : 1;
+  for (int64_t k0 = 0; k0 < K; k0 += kc) {
+    const int64_t kk = (K - k0 < kc) ? K - k0 : kc;
+    if ((rc = oz_slice_panel(A + k0, lda, M, kk, wsa, M, em.slices, stream))) return rc;
+    if (!same && (rc = oz_slice_panel(B + k0, ldb, N, kk, wsb, N, em.slices, stream))) return rc;
+    if ((rc = oz_gemm_sliced(M, N, kk, alpha, wsa, M, 0, same ? wsa : wsb, same ? M : N, 0, k0 == 0 ? beta : 1.0, C, ldc, lower,
+                             em.slices, stream)))
+      return rc;
+  }
+  return 1;
 }
 
 }  // namespace gpk

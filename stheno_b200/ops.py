@@ -403,7 +403,8 @@ def _emulation_for_gemm(device, dtype, M, N, K):
     if dtype != torch.float64:
         return
     slices = _oz_slices()
-    need = _lib.load().gpk_f64_emulation_scratch_bytes(M, N, K, slices) if slices and M * N * K >= 1.5e9 else 0
+    kc = K if K <= 65536 else -(-K // (-(-K // 65536)) // 128) * 128 + 128  # long reductions run in K chunks <= 65536
+    need = _lib.load().gpk_f64_emulation_scratch_bytes(M, N, min(K, kc), slices) if slices and M * N * K >= 1.5e9 else 0
     _set_emulation(device, slices, need)
 
 

@@ -150,3 +150,26 @@ def test_emulation_switch_is_per_call(S, ops):
         S.B.precision = before
     assert a == c
     assert abs(a - b) / abs(a) < 1e-11
+
+
+def test_long_reduction_runs_in_k_chunks(S, ops):
+    """K > 65536 (the sparse path's n = 262144 reductions): the emulated GEMM behind ``gemm_nt`` splits K into passes that
+    each keep the int32 accumulation exact."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    M, N, K = 256, 384, 131072 + 128
+    A = torch.randn(1, M, K, device="cuda", dtype=torch.float64, generator=g)
+    Bm = torch.randn(1, N, K, device="cuda", dtype=torch.float64, generator=g)
+    C0 = torch.randn(1, M, N, device="cuda", dtype=torch.float64, generator=g)
+    ref = 0.5 * C0 + 2.0 * (A @ Bm.transpose(1, 2))
+    before = S.B.precision
+    try:
+        S.B.precision = "fp64"
+        native = ops.gemm_nt(A, Bm, C0.clone(), alpha=2.0, beta=0.5)
+        S.B.precision = "auto"
+        emu = ops.gemm_nt(A, Bm, C0.clone(), alpha=2.0, beta=0.5)
+    finally:
+        S.B.precision = before
+    scale = ref.abs().max().item()
+    assert (native - ref).abs().max().item() / scale < 1e-13
+    assert (emu - ref).abs().max().item() / scale < 1e-12
+    assert not torch.equal(emu, native)  # it really took the emulated path
