@@ -9,6 +9,8 @@ from oracle import gp_oracle as O
 
 pytestmark = pytest.mark.gpu
 
+from tests._oz_model import gemm as oz_model_gemm  # noqa: E402  (NumPy integer model of the kernel)
+
 
 @pytest.fixture(scope="module")
 def S():
@@ -173,3 +175,19 @@ def test_long_reduction_runs_in_k_chunks(S, ops):
     assert (native - ref).abs().max().item() / scale < 1e-13
     assert (emu - ref).abs().max().item() / scale < 1e-12
     assert not torch.equal(emu, native)  # it really took the emulated path
+
+
+@pytest.mark.parametrize("slices", [6, 7, 8])
+@pytest.mark.parametrize("alpha,beta", [(1.0, 0.0), (-1.0, 1.0), (-1.5, 0.5)])
+def test_gemm_oz_bit_exact_vs_integer_model(ops, slices, alpha, beta):
+    """Every inexact step of the emulation is ONE correctly rounded fp64 operation (the slice products are exact integers),
+    so the kernel must reproduce the NumPy integer model bit for bit."""
+    rng = np.random.default_rng(slices)
+    M, N, K = 256, 192, 384
+    A = rng.standard_normal((M, K)) * np.exp(2 * rng.standard_normal((M, 1)))
+    B = rng.standard_normal((N, K))
+    C0 = rng.standard_normal((M, N))
+    want = oz_model_gemm(A, B, C0, alpha, beta, slices)
+    dev = lambda a: torch.as_tensor(a, device="cuda")
+    got = ops.gemm_nt_oz(dev(A), dev(B), dev(C0).clone(), alpha=alpha, beta=beta, slices=slices).cpu().numpy()
+    assert np.array_equal(got, want), np.abs(got - want).max()
