@@ -10,9 +10,14 @@ epsilon = 1e-12
 #: Arithmetic of the LARGE GEMM-shaped updates of float64 problems (Cholesky trailing updates for n >= 2048, the GEMMs of
 #: the triangular solves and ``gemm_nt`` with M N K >= 1.5e9; single-matrix problems).  Everything else -- kernel-matrix
 #: build, leaf factorisations, panel solves, small problems, batched problems -- always runs in native fp64.
-#:   "auto" (default) = "int8x7": fp64 emulated on the int8 tensor cores (tcgen05.mma.kind::i8): operands split error-free
-#:       into 7 signed 7-bit slices (49 bits), EXACT int32 slice products, fp64 recombination.  Product error ~3e-14 |a||b|;
-#:       log-pdfs agree with the native path to ~1e-13 relative -- three orders inside the 1e-10 parity bar.  ~2x faster.
+#:   "auto" (default): fp64 emulated on the int8 tensor cores (tcgen05.mma.kind::i8): operands split error-free into signed
+#:       7-bit slices, EXACT int32 slice products, fp64 recombination.  7 slices (49 bits, product error ~3e-14 |a||b|) for
+#:       products that do not feed a factorisation and for factorisations of matrices that are well conditioned by
+#:       construction (known scalar noise >= 1e-6 of the kernel variance): log-pdfs agree with the native path to ~1e-13
+#:       relative -- three orders inside the 1e-10 parity bar, ~2x faster.  8 slices (below) for every other factorisation
+#:       (noise-free kernels on the 1e-12 jitter, posterior covariances, assembled multi-output joints): those can be
+#:       numerically singular, where only fp64-grade products keep the pivots positive when native fp64 does.
+#:   "int8x7": 7 slices everywhere the emulation applies.
 #:   "int8x8": 8 slices (56 bits >= the 53 of fp64): product error ~1e-15, the same as the fp64 tensor-core kernel itself.
 #:   "int8x6": 6 slices (42 bits): ~4e-12 products, log-pdfs ~4e-10 -- faster still, NOT inside the parity bar.
 #:   "fp64": native fp64 tensor cores (DMMA) everywhere.

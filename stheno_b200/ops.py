@@ -343,7 +343,7 @@ def _new_workspace(B, n, k, device, dtype, rhs_t):
     return W, n_pad, extra
 
 
-def _potrf(W, n, n_pad, extra, k):
+def _potrf(W, n, n_pad, extra, k, well_conditioned=False):
     B = W.shape[0]
     logdet = torch.zeros(B, device=W.device, dtype=W.dtype)
     info = torch.zeros(B, device=W.device, dtype=torch.int32)
@@ -357,7 +357,7 @@ def _potrf(W, n, n_pad, extra, k):
         check(rc, "gpk_potrf_f64_tf32x3")
         return Chol(W, n, k, logdet, info)
     if W.dtype == torch.float64 and B == 1 and n_pad >= 2048:
-        slices = _oz_slices()
+        slices = _oz_slices(well_conditioned)
         _set_emulation(W.device, slices, _lib.load().gpk_potrf_oz_ws_bytes(n_pad, extra, slices) if slices else 0)
     rc = _fn("gpk_potrf", W.dtype)(_ptr(W), W.stride(1), W.stride(0), n_pad, extra, _ptr(logdet), _ptr(info), B,
                                    _stream())
@@ -365,11 +365,37 @@ def _potrf(W, n, n_pad, extra, k):
     return Chol(W, n, k, logdet, info)
 
 
-def _oz_slices():
-    """``B.precision`` -> number of int8 slices of the emulated large fp64 updates (0: native fp64 tensor cores only)."""
+def _oz_slices(well_conditioned=True):
+    """``B.precision`` -> number of int8 slices of the emulated large fp64 updates (0: native fp64 tensor cores only).
+
+    "auto" uses 7 slices (49-bit operands, product error ~3e-14) for products that do not feed a factorisation and for
+    factorisations of matrices that are well conditioned BY CONSTRUCTION (a known scalar noise / jitter of at least 1e-6 of the
+    kernel's variance on the diagonal), and 8 slices (56-bit operands, the accuracy of the fp64 tensor-core kernel itself)
+    for every other factorisation: numerically singular covariances (noise-free kernels with the 1e-12 jitter, posterior
+    covariances) sit so close to losing positive definiteness that the 100x larger backward error of 7 slices can tip a
+    pivot negative where native fp64 just survives (measured: ``tools/oz_illcond.py``)."""
     from . import B as _Bns
 
-    return {"auto": 7, "int8x5": 5, "int8x6": 6, "int8x7": 7, "int8x8": 8}.get(getattr(_Bns, "precision", "auto"), 0)
+    mode = getattr(_Bns, "precision", "auto")
+    if mode == "auto":
+        return 7 if well_conditioned else 8
+    return {"int8x5": 5, "int8x6": 6, "int8x7": 7, "int8x8": 8}.get(mode, 0)
+
+
+def _well_conditioned(flat, noise_scalar, noise_vec, jitter):
+    """True when ``k(x, x) + noise`` is well conditioned by construction: scalar diagonal term >= 1e-6 of the kernel's
+    variance scale (sum of |coefficients| of the bounded stationary terms; anything with a Linear factor is unbounded)."""
+    if noise_vec is not None:
+        return False
+    scale = 0.0
+    for coef, fs in flat.terms:
+        if any(kind == "linear" for kind, _ in fs):
+            return False
+        if all(kind == "delta" for kind, _ in fs):
+            continue  # a Delta term only adds to the diagonal
+        scale += abs(coef)
+    diag = float(noise_scalar) + float(jitter) + sum(c for c, fs in flat.terms if fs and all(k == "delta" for k, _ in fs) and c > 0)
+    return diag >= 1e-6 * max(scale, 1e-300)
 
 
 #: per-device scratch handed to the library for the int8-slice emulation: [tensor, slices registered]
@@ -441,7 +467,7 @@ def chol_from_kernel(flat, xg, *, noise_scalar=0.0, noise_vec=None, jitter=0.0, 
     W, n_pad, extra = _new_workspace(B, n, k, xg.device, xg.dtype, rhs_t)
     _km_launch(flat, xg, xg, n, n, d, KM_LOWER | KM_SAME | KM_PAD_IDENTITY, noise_scalar, noise_vec, jitter, W,
                W.stride(1), W.stride(0), B)
-    return _potrf(W, n, n_pad, extra, k)
+    return _potrf(W, n, n_pad, extra, k, _well_conditioned(flat, noise_scalar, noise_vec, jitter))
 
 
 def chol_from_dense(K, *, jitter=0.0, rhs_t=None):

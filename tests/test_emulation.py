@@ -191,3 +191,25 @@ def test_gemm_oz_bit_exact_vs_integer_model(ops, slices, alpha, beta):
     dev = lambda a: torch.as_tensor(a, device="cuda")
     got = ops.gemm_nt_oz(dev(A), dev(B), dev(C0).clone(), alpha=alpha, beta=beta, slices=slices).cpu().numpy()
     assert np.array_equal(got, want), np.abs(got - want).max()
+
+
+def test_auto_picks_slices_by_conditioning(S):
+    """"auto" = 7 slices when the matrix is well conditioned by construction (known scalar noise), 8 slices (the accuracy of
+    the fp64 tensor-core kernel itself) for factorisations that may be numerically singular: noise-free kernels with the
+    1e-12 jitter lose positive definiteness under the 100x larger backward error of 7 slices (tools/oz_illcond.py)."""
+    rng = np.random.default_rng(4)
+    n = 2304
+    x = torch.as_tensor(rng.uniform(0, 10, (n, 2)), device="cuda")
+    y = torch.as_tensor(rng.standard_normal(n), device="cuda")
+    f = S.GP(S.EQ().stretch(0.1))  # short length scale: the noise-free matrix is comfortably positive definite
+    before = S.B.precision
+    out = {}
+    try:
+        for prec in ("auto", "int8x7", "int8x8"):
+            S.B.precision = prec
+            out[prec] = (f(x).logpdf(y).item(), f(x, 0.1).logpdf(y).item())
+    finally:
+        S.B.precision = before
+    assert out["auto"][0] == out["int8x8"][0]  # noise-free: 8 slices
+    assert out["auto"][1] == out["int8x7"][1]  # known noise: 7 slices
+    assert out["int8x7"][1] != out["int8x8"][1]
