@@ -5,9 +5,13 @@
 //                                  (cyclic 8 x 8 micro-tiles, one __syncthreads per column, log-det and info folded in)
 //                (2) trsm_leaf   : all rows below (incl. the fused right-hand-side rows)  X L11^T = A21
 //                (3) gemm (K=128): update of the rest of the outer panel
-//              and per outer panel one big SYRK-style trailing update (K = 512) on the fp64 tensor cores, which
-//              carries > 90 % of the n^3/3 flops at n = 16384 with C read/written once per 512 columns
-//              (measured: 512 beats 1024 and 2048 -- less latency-bound in-panel work, GEMM still at 33+ TFLOP/s).
+//              and per outer panel one big SYRK-style trailing update (K = 512), which carries > 90 % of the n^3/3 flops
+//              at n = 16384 with C read/written once per 512 columns: on the int8 tensor cores (fp64 emulated with exact
+//              integer slice products, gemm_oz.cu) when the caller enabled it, on the fp64 tensor cores (DMMA) otherwise
+//              (measured: 512 beats 256, 768, 1024 for both).
+//              With look-ahead the next panel is factorised on two high-priority side streams while that update runs:
+//              `chain` = leaf -> 4-CTA solve of the next 128 rows -> 17-CTA update of the next diagonal block -> leaf ...
+//              (everything the next leaf depends on), `bulk` = all other rows of the block column, ordered by events.
 //   trsm_right recursive halving down to the 128-wide leaf; all off-diagonal work is gemm_nt with K >= 128.
 //
 // Right-hand sides ride along as extra ROWS below the matrix (b^T), so L^-1 b falls out of the factorisation
