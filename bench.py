@@ -208,6 +208,17 @@ OZ_TRAFFIC_SAMPLE = {"from": "profiles/r01_ncu_oz_gemm_details.csv (ncu --set fu
                      "dram_bytes": 520.2e6, "algorithmic_bytes": 7 * 8192 * 512 + 2 * 8 * (8192 * 8192 // 2)}
 
 
+def alt_int8_peak(achieved):
+    """The same fraction against 2 x the driver-written bf16 number of MEASURED_PEAKS.json (int8 runs at twice the bf16 rate)."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            mp = json.load(fh)
+        alt = 2.0 * float(mp["bf16_tflops"])
+        return {"peak_2x_bf16_measured_peaks_json": alt, "frac_vs_2x_bf16_measured_peaks_json": achieved / alt}
+    except Exception:
+        return {}
+
+
 def int8_peak_tops(dev):
     """Dense int8 tensor-core throughput measured in-run with the library GEMM (torch._int_mm -> cuBLASLt), the int8
     counterpart of MEASURED_PEAKS.json's bf16 entry; falls back to 2 x that entry."""
@@ -352,6 +363,7 @@ def gpu_arm(args, rank, world, local_rank):
                           f"the Cholesky as {n_prod} exact int8 slice products per fp64 product)",
                 "peak_source": peak_src,
                 "fp64_equivalent_tflops": eq_tflops, "int8_products_per_fp64_product": n_prod,
+                **alt_int8_peak(achieved),
                 "launches_per_step": o_launches / prof_steps, "kernel_ms_per_step": o_ms / prof_steps,
                 "traffic_sample": OZ_TRAFFIC_SAMPLE,
                 "whole_step_tflops_fp64_equivalent": cost(N_FULL) / (ms / args.steps * 1e-3) / 1e12,
