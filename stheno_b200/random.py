@@ -193,9 +193,16 @@ class Normal(RandomVector):
         var = self._var_dev()
         xd = xd.to(var.dtype)
         if xd.dim() == 2 and xd.shape[1] == 1:
-            # One tiny device reduction + flag read instead of shipping the mask.
-            nan = torch.isnan(xd[:, 0])
-            if bool(nan.any()):
+            # Missing data: host-resident observations are checked on the host (no device round trip); device-resident
+            # ones with one tiny device reduction + flag read instead of shipping the mask.
+            if isinstance(x, torch.Tensor) and x.is_cuda:
+                nan = torch.isnan(xd[:, 0])
+                has_nan = bool(nan.any())
+            else:
+                host = x.detach().numpy() if isinstance(x, torch.Tensor) else np.asarray(x, dtype=float)
+                has_nan = bool(np.isnan(host).any())
+                nan = torch.isnan(xd[:, 0]) if has_nan else None
+            if has_nan:
                 avail = ~nan
                 sub = Normal(self._mean_dev()[avail], M.submatrix(var, avail), origin=self._origin)
                 return sub.logpdf(from_dev(xd[avail], out_origin))
