@@ -41,3 +41,30 @@ def test_model_is_exact_on_small_integers():
     A = rng.integers(-1000, 1000, (32, 128)).astype(np.float64)
     B = rng.integers(-1000, 1000, (48, 128)).astype(np.float64)
     assert np.array_equal(gemm(A, B, None, 1.0, 0.0, 7), A @ B.T)
+
+
+def test_auto_slice_count_heuristic():
+    """``B.precision = "auto"``: 7 slices only for factorisations that are well conditioned by construction."""
+    from stheno_b200 import B, ops
+
+    eq = ops.FlatKernel([(1.0, [("eq", 0)])], 1)
+    eq_delta = ops.FlatKernel([(2.0, [("eq", 0)]), (0.1, [("delta", 0)])], 1)
+    lin = ops.FlatKernel([(1.0, [("linear", 0)])], 1)
+    assert ops._well_conditioned(eq, 0.1, None, 1e-12)
+    assert ops._well_conditioned(eq_delta, 0.0, None, 1e-12)  # the Delta term is the noise
+    assert not ops._well_conditioned(eq, 0.0, None, 1e-12)  # noise-free: only the jitter
+    assert not ops._well_conditioned(eq, 1e-9, None, 0.0)
+    assert not ops._well_conditioned(eq, 0.1, object(), 0.0)  # per-point noise: smallest entry unknown on the host
+    assert not ops._well_conditioned(lin, 0.1, None, 0.0)  # unbounded kernel
+    before = B.precision
+    try:
+        B.precision = "auto"
+        assert ops._oz_slices(True) == 7 and ops._oz_slices(False) == 8
+        B.precision = "int8x6"
+        assert ops._oz_slices(True) == 6 and ops._oz_slices(False) == 6
+        B.precision = "fp64"
+        assert ops._oz_slices(True) == 0
+        B.precision = "tf32x3"
+        assert ops._oz_slices(False) == 0
+    finally:
+        B.precision = before
