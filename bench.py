@@ -323,18 +323,28 @@ def gpu_arm(args, rank, world, local_rank):
     value = world * args.steps / (ms * 1e-3)
     e2e_value = world * args.steps / (ms_e2e * 1e-3)
 
-    # the same step on the native fp64 tensor-core path (B.precision = "fp64"), for the record
-    native = None
-    if S.B.precision != "fp64":
+    # the same step on the native fp64 tensor-core path (B.precision = "fp64") and with 8 slices (56-bit operands, i.e. no
+    # fewer bits than fp64's 53), for the record
+    def other_mode(mode, note):
         chosen = S.B.precision
-        S.B.precision = "fp64"
-        for _ in range(2):
-            lp_native = step_resident()
-        ms_n, lp_native, _ = timed(step_resident, min(args.steps, 5))
-        S.B.precision = chosen
-        native = {"value": world * min(args.steps, 5) / (ms_n * 1e-3), "unit": UNIT, "ms_per_step": ms_n / min(args.steps, 5),
-                  "logpdf": float(lp_native), "logpdf_rel_diff": abs(float(lp) - float(lp_native)) / abs(float(lp_native)),
-                  "note": "B.precision='fp64': DMMA trailing updates (python bench.py --precision fp64 makes it the headline)"}
+        S.B.precision = mode
+        try:
+            for _ in range(2):
+                step_resident()
+            k = min(args.steps, 5)
+            ms_m, lp_m, _ = timed(step_resident, k)
+        finally:
+            S.B.precision = chosen
+        return {"value": world * k / (ms_m * 1e-3), "unit": UNIT, "ms_per_step": ms_m / k, "logpdf": float(lp_m),
+                "logpdf_rel_diff": abs(float(lp) - float(lp_m)) / abs(float(lp_m)), "note": note}
+
+    native = eight = None
+    if S.B.precision != "fp64":
+        native = other_mode("fp64", "B.precision='fp64': DMMA trailing updates (python bench.py --precision fp64 makes it the headline); "
+                                    "logpdf_rel_diff = headline log-pdf vs this one")
+    if S.B.precision in ("auto", "int8x7"):
+        eight = other_mode("int8x8", "B.precision='int8x8': the same emulation with 8 slices = 56-bit operands (>= fp64's 53), product "
+                                     "error ~1e-15 like the DMMA kernel itself (python bench.py --precision int8x8)")
 
     if rank == 0:
         # roofline leg: dominant kernel timed in situ with events on its own stream (look-ahead off for these steps: with
@@ -395,7 +405,7 @@ def gpu_arm(args, rank, world, local_rank):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "arithmetic": ARITHMETIC.get(S.B.precision, S.B.precision), "precision_mode": S.B.precision,
-            "native_fp64": native,
+            "native_fp64": native, "emulated_8_slices": eight,
             "config": {"workload": "EQ().stretch(2.0)+0.1*Delta(), n=16384, d=8, fp64: kernel build + Cholesky + logpdf",
                        "parallelism": "single GPU" if world == 1 else f"replicas only x{world} (independent problems, no data-path collective)",
                        "l2": "working set 2.1 GB per step >> 126 MB L2 (no flush needed)", "n": N_FULL, "d": D},
