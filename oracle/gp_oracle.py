@@ -107,6 +107,9 @@ def ew_dists(x, y):
 # A kernel is a nested tuple:
 #   ("eq",) ("matern12",) ("matern32",) ("matern52",) ("linear",) ("delta",) ("one",) ("zero",)
 #   ("scaled", c, k)  ("sum", k1, k2)  ("product", k1, k2)  ("stretched", ell, k)
+#   input maps (``GP.shift/select/transform``, ``stheno/model/measure.py:272-345``; the second entry of a pair maps the second
+#   argument, ``None`` = untouched):  ("shifted", c, k)  ("selected", dims, k)  ("transformed", f, k)  and per-argument
+#   ("shifted2", (c1, c2), k)  ("selected2", (dims1, dims2), k)  ("transformed2", (f1, f2), k)  ("stretched2", (l1, l2), k)
 # Call sites in the reference: ``stheno/model/fdd.py:66,79``,
 # ``stheno/model/observations.py:139,285,286,304``.
 # --------------------------------------------------------------------------------------
@@ -148,6 +151,27 @@ def _kernel(spec, x, y, d2fn, dfn, same):
     if kind == "stretched":
         ell = np.asarray(spec[1], dtype=np.float64)
         return _kernel(spec[2], _uprank(x) / ell, _uprank(y) / ell, d2fn, dfn, same)
+    if kind in ("shifted", "selected", "transformed", "shifted2", "selected2", "transformed2", "stretched2"):
+        # mlkernels ShiftedKernel / SelectedKernel / InputTransformedKernel / StretchedKernel [UPSTREAM-RECALLED]:
+        # k(x - c, y - c), k(x[:, dims], y[:, dims]), k(f(x), f(y)); the "...2" forms take one parameter per argument
+        # (None = that argument untouched), as the cross-kernels of ``measure.py:286,305,324,343`` do.
+        two = kind.endswith("2")
+        base = kind[:-1] if two else kind
+        p1, p2 = spec[1] if two else (spec[1], spec[1])
+
+        def apply(a, p):
+            a = _uprank(a)
+            if p is None:
+                return a
+            if base == "shifted":
+                return a - np.asarray(p, np.float64)
+            if base == "selected":
+                return a[..., list(p)]
+            if base == "stretched":
+                return a / np.asarray(p, np.float64)
+            return _uprank(np.asarray(p(a), np.float64))
+
+        return _kernel(spec[2], apply(x, p1), apply(y, p2), d2fn, dfn, same and not two)
     raise ValueError(f"unknown kernel {kind!r}")
 
 

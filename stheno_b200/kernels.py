@@ -139,6 +139,21 @@ class Kernel:
             return _simplify_stretch(self, stretches[0], stretches[0])
         return _simplify_stretch(self, stretches[0], stretches[1])
 
+    def shift(self, *shifts):
+        """``k.shift(c)``: ``k(x - c, y - c)``; ``k.shift(c1, c2)`` shifts the inputs separately (``measure.py:286``)."""
+        return _map_kernel(self, "shift", shifts)
+
+    def select(self, *dims):
+        """``k.select(dims)``: ``k(x[:, dims], y[:, dims])``; ``k.select(dims1, dims2)`` per input, ``None`` = all
+        (``measure.py:324``).  ``dims``: a tuple / list of column indices."""
+        dims = tuple(None if d is None else tuple(np.atleast_1d(d).tolist()) for d in dims)
+        return _map_kernel(self, "select", dims)
+
+    def transform(self, *fs):
+        """``k.transform(f)``: ``k(f(x), f(y))``; ``k.transform(f1, f2)`` per input, ``None`` = identity (``measure.py:343``).
+        ``f`` receives the points as a device tensor ``[..., n, d]`` and returns a tensor (or anything array-like)."""
+        return _map_kernel(self, "transform", fs)
+
     def __add__(self, other):
         other = _as_kernel(other)
         if isinstance(other, ZeroKernel):
@@ -530,6 +545,131 @@ class ReversedKernel(Kernel):
         return f"Reversed({self.k.render()})"
 
 
+# ------------------------------------------------------------------------------------------------------------
+# input maps: shift / select / transform / per-argument stretch  (``GP.shift/select/transform``,
+# ``stheno/model/measure.py:272-345``; mlkernels ShiftedKernel / SelectedKernel / InputTransformedKernel)
+# ------------------------------------------------------------------------------------------------------------
+class InputMap:
+    """A transformation of the input points applied on the device before the kernel / mean is evaluated:
+    ``shift``: ``x - c``; ``stretch``: ``x / l``; ``select``: ``x[:, dims]``; ``transform``: ``f(x)``."""
+
+    def __init__(self, kind, param):
+        self.kind, self.param = kind, param
+
+    def __call__(self, x):
+        t = x.t
+        p = self.param
+        if self.kind == "shift":
+            v = p if isinstance(p, torch.Tensor) else torch.as_tensor(np.asarray(p, np.float64), dtype=t.dtype, device=t.device)
+            out = t - v.to(device=t.device, dtype=t.dtype)
+        elif self.kind == "stretch":
+            v = p if isinstance(p, torch.Tensor) else torch.as_tensor(np.asarray(p, np.float64), dtype=t.dtype, device=t.device)
+            out = t / v.to(device=t.device, dtype=t.dtype)
+        elif self.kind == "select":
+            out = t[..., list(p)]
+        else:
+            out = p(t)
+            if not isinstance(out, torch.Tensor):
+                out = to_dev(out, t.dtype)
+            out = uprank(out.to(t.dtype))
+        y = Input.__new__(Input)
+        y.origin, y._groups, y.src = x.origin, {}, None
+        y.t = out.contiguous()
+        return y
+
+    def same_as(self, other):
+        if other is None or self.kind != other.kind:
+            return False
+        a, b = self.param, other.param
+        if a is b:
+            return True
+        if self.kind == "transform" or isinstance(a, torch.Tensor) or isinstance(b, torch.Tensor):
+            return False
+        return np.array_equal(np.asarray(a, dtype=object), np.asarray(b, dtype=object))
+
+    def render(self):
+        sym = {"shift": "shift", "stretch": ">", "select": ":", "transform": "transform"}[self.kind]
+        if self.kind == "transform":
+            return f"{sym} {getattr(self.param, '__name__', 'f')}"
+        if self.kind == "select":
+            return f"{sym} {list(self.param)}"
+        return f"{sym} {_fmt(self.param)}"
+
+
+def _same_map(a, b):
+    return (a is None and b is None) or (a is not None and a.same_as(b))
+
+
+class MappedKernel(Kernel):
+    """``k(m1(x), m2(y))`` for input maps ``m1``, ``m2`` (``None`` = identity).  With equal maps on the same points the inner
+    kernel keeps its fused path (symbolic :class:`KernelDense`: K1 writes straight into the Cholesky workspace)."""
+
+    def __init__(self, k, m1, m2):
+        self.k, self.m1, self.m2 = k, m1, m2
+
+    @property
+    def symmetric(self):
+        return self.k.symmetric and _same_map(self.m1, self.m2)
+
+    def reversed(self):
+        return self if self.symmetric else MappedKernel(self.k.reversed(), self.m2, self.m1)
+
+    def _mapped(self, x, y, same):
+        xs = x if self.m1 is None else self.m1(x)
+        if same and _same_map(self.m1, self.m2):
+            return xs, xs, True
+        ys = y if self.m2 is None else self.m2(y)
+        return xs, ys, False
+
+    def _pairwise_dev(self, x, y, same):
+        return self.k._pairwise_dev(*self._mapped(x, y, same))
+
+    def _elwise_dev(self, x, y, same):
+        return self.k._elwise_dev(*self._mapped(x, y, same))
+
+    def _matrix(self, x, y, same):
+        xs, ys, still_same = self._mapped(x, y, same)
+        if still_same:
+            return self.k._matrix(xs, xs, True)
+        return M.Dense(self.k._pairwise_dev(xs, ys, False), x.origin)
+
+    def render(self):
+        if _same_map(self.m1, self.m2):
+            return f"{_paren(self.k)} {self.m1.render()}"
+        r = lambda m: "id" if m is None else m.render()
+        return f"{_paren(self.k)} ({r(self.m1)}, {r(self.m2)})"
+
+    @property
+    def stationary(self):
+        return self.k.stationary and _same_map(self.m1, self.m2) and self.m1 is not None and self.m1.kind in ("shift", "stretch")
+
+
+def _map_kernel(k, kind, params):
+    """``k.shift(c)`` / ``k.shift(c1, c2)`` etc.: one parameter maps both arguments, two map them separately and ``None`` (or, for
+    stretches, 1 / for shifts, 0) leaves an argument untouched."""
+    if isinstance(k, ZeroKernel):
+        return k
+    if len(params) == 1:
+        m = InputMap(kind, params[0])
+        return MappedKernel(k, m, m)
+    if len(params) != 2:
+        raise ValueError(f"{kind}: one parameter (both inputs) or two (one per input) expected")
+
+    def one(p):
+        if p is None:
+            return None
+        if kind == "shift" and np.isscalar(p) and p == 0:
+            return None
+        if kind == "stretch" and np.isscalar(p) and p == 1:
+            return None
+        return InputMap(kind, p)
+
+    m1, m2 = one(params[0]), one(params[1])
+    if m1 is None and m2 is None:
+        return k
+    return MappedKernel(k, m1, m2)
+
+
 def _strip_scale(k):
     c = 1.0
     while isinstance(k, ScaledKernel):
@@ -542,7 +682,7 @@ def _simplify_stretch(k, s1, s2):
     if isinstance(k, (ZeroKernel, OneKernel)):
         return k
     if s1 is not s2 and not (np.isscalar(s1) and np.isscalar(s2) and s1 == s2):
-        raise NotImplementedError("different stretches for the two kernel inputs are outside the hot-path scope")
+        return _map_kernel(k, "stretch", (s1, s2))  # per-argument stretch (cross-kernels of a stretched GP, measure.py:305)
     return StretchedKernel(k, s1)
 
 
@@ -783,6 +923,15 @@ class Mean:
     def stretch(self, stretch):
         return self if self.is_zero else StretchedMean(self, stretch)
 
+    def shift(self, shift):
+        return self if self.is_zero else MappedMean(self, InputMap("shift", shift))
+
+    def select(self, dims):
+        return self if self.is_zero else MappedMean(self, InputMap("select", tuple(np.atleast_1d(dims).tolist())))
+
+    def transform(self, f):
+        return self if self.is_zero else MappedMean(self, InputMap("transform", f))
+
     def render(self):
         return type(self).__name__ + "()"
 
@@ -868,6 +1017,19 @@ class StretchedMean(Mean):
                                                                    device=x.t.device)
         xs.t = x.t / sv
         return self.m._dev(xs)
+
+
+class MappedMean(Mean):
+    """``m(map(x))`` (``GP.shift/select/transform`` on the mean, ``stheno/model/measure.py:284,322,341``)."""
+
+    def __init__(self, m, imap):
+        self.m, self.imap = m, imap
+
+    def _dev(self, x):
+        return self.m._dev(self.imap(x))
+
+    def render(self):
+        return f"{self.m.render()} {self.imap.render()}"
 
 
 class FunctionMean(Mean):

@@ -128,10 +128,31 @@ class GP(RandomProcess):
             measure.stretch(res, self, stretch)
         return res
 
+    def shift(self, shift):
+        """``f.shift(c)``: ``x -> f(x - c)`` (``gp.py:190-195``)."""
+        res = GP()
+        for measure in self._measures:
+            measure.shift(res, self, shift)
+        return res
+
+    def select(self, *dims):
+        """``f.select(*dims)``: a GP of only those input dimensions (``gp.py:211-216``)."""
+        res = GP()
+        for measure in self._measures:
+            measure.select(res, self, *dims)
+        return res
+
+    def transform(self, f):
+        """``f.transform(g)``: ``x -> f(g(x))`` (``gp.py:204-209``)."""
+        res = GP()
+        for measure in self._measures:
+            measure.transform(res, self, f)
+        return res
+
     def _out_of_scope(self, *a, **k):
         raise NotImplementedError("outside the GP-inference hot-path scope (SURVEY.md 8f rank 3)")
 
-    shift = transform = select = diff = diff_approx = _out_of_scope
+    diff = diff_approx = _out_of_scope
 
     @property
     def stationary(self):

@@ -143,6 +143,33 @@ class Measure:
             lambda j: self.kernels[p, j].stretch(stretch, 1),
         )
 
+    def shift(self, p_shifted, p, shift):
+        """``measure.py:272-287``."""
+        return self._update(
+            p_shifted,
+            self.means[p].shift(shift),
+            self.kernels[p].shift(shift),
+            lambda j: self.kernels[p, j].shift(shift, 0),
+        )
+
+    def select(self, p_selected, p, *dims):
+        """``measure.py:307-325``."""
+        return self._update(
+            p_selected,
+            self.means[p].select(dims),
+            self.kernels[p].select(dims),
+            lambda j: self.kernels[p, j].select(dims, None),
+        )
+
+    def transform(self, p_transformed, p, f):
+        """``measure.py:327-345``."""
+        return self._update(
+            p_transformed,
+            self.means[p].transform(f),
+            self.kernels[p].transform(f),
+            lambda j: self.kernels[p, j].transform(f, None),
+        )
+
     def condition(self, *args):
         """``measure | obs`` -> posterior measure whose means / kernels are built on demand (``measure.py:362-401``)."""
         if len(args) == 1 and isinstance(args[0], AbstractObservations):

@@ -1,0 +1,129 @@
+"""``GP.shift / select / transform`` and the per-argument kernel maps behind them (SURVEY 8f rank 3;
+``stheno/model/measure.py:272-345``, ``stheno/model/gp.py:190-216``) against the oracle.
+
+Every test runs twice: on the CPU with the torch stand-in backend (host logic; ``-m "not gpu"``) and on the GPU through
+the real CUDA kernels (``-m gpu``)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp_oracle as O
+
+
+@pytest.fixture(params=["cpu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def S(request, monkeypatch):
+    import stheno_b200 as s
+
+    if request.param == "cpu":
+        from tests import _cpu_backend
+
+        _cpu_backend.install(monkeypatch)
+    s.B.epsilon = 1e-12
+    monkeypatch.setattr(s.Measure, "default", None)
+    return s
+
+
+def approx(a, b, rtol=1e-9, atol=1e-9):
+    import stheno_b200 as s
+
+    np.testing.assert_allclose(np.asarray(s.B.to_numpy(a)), np.asarray(s.B.to_numpy(b)), rtol=rtol, atol=atol)
+
+
+RNG = np.random.default_rng(12)
+X = RNG.uniform(-2, 2, (40, 3))
+Y = RNG.uniform(-2, 2, (25, 3))
+
+
+def sq(t):  # works on torch tensors (the library) and numpy arrays (the oracle)
+    return t**2
+
+
+def test_kernel_maps_pairwise_and_elwise(S):
+    base = S.EQ().stretch(1.3) + 0.5 * S.Linear()
+    spec = ("sum", ("stretched", 1.3, ("eq",)), ("scaled", 0.5, ("linear",)))
+    cases = [
+        (base.shift(0.7), ("shifted", 0.7, spec)),
+        (base.shift(np.array([0.1, -0.2, 0.3])), ("shifted", np.array([0.1, -0.2, 0.3]), spec)),
+        (base.select((0, 2)), ("selected", (0, 2), spec)),  # one tuple = both inputs (two arguments = one per input)
+        (base.select([1]), ("selected", (1,), spec)),
+        (base.transform(sq), ("transformed", sq, spec)),
+        (base.shift(0.7, 0), ("shifted2", (0.7, None), spec)),
+        (base.shift(0.4, -0.3), ("shifted2", (0.4, -0.3), spec)),
+        (base.select((0, 1), None), ("selected2", ((0, 1), None), spec)),
+        (base.transform(sq, None), ("transformed2", (sq, None), spec)),
+        (base.stretch(2.0, 1), ("stretched2", (2.0, None), spec)),
+        (base.stretch(2.0, 0.5), ("stretched2", (2.0, 0.5), spec)),
+    ]
+    for k, ospec in cases:
+        if ospec[0] == "selected2":  # k(x[:, :2], y) needs matching widths: compare on 2-column second arguments
+            approx(k(X, Y[:, :2]), O.kernel_matrix(ospec, X, Y[:, :2]))
+            continue
+        approx(k(X, Y), O.kernel_matrix(ospec, X, Y))
+        approx(S.B.dense(k(X)), O.kernel_matrix(ospec, X) if not ospec[0].endswith("2") else O.kernel_matrix(ospec, X, X))
+        approx(k.elwise(X, X + 0.1), O.kernel_elwise(ospec, X, X + 0.1))
+
+
+def test_maps_compose_and_stay_symmetric(S):
+    k = S.Matern52().stretch(0.8).shift(1.0).select((2, 0))
+    spec = ("selected", (2, 0), ("shifted", 1.0, ("stretched", 0.8, ("matern52",))))
+    approx(S.B.dense(k(X)), O.kernel_matrix(spec, X))
+    assert k.symmetric and k.reversed() is k
+    k2 = S.EQ().shift(0.5, 0)
+    assert not k2.symmetric
+    approx(k2.reversed()(X, Y), O.kernel_matrix(("shifted2", (None, 0.5), ("eq",)), X, Y))
+    assert isinstance(S.EQ().shift(0, 0), type(S.EQ()))  # identity maps drop out
+
+
+def test_gp_shift_select_transform_logpdf_and_posterior(S):
+    y = np.sin(X[:, 0]) + 0.1 * RNG.standard_normal(len(X))
+    xs = RNG.uniform(-2, 2, (15, 3))
+    kspec = ("stretched", 0.9, ("matern32",))
+    for make, wrap in [
+        (lambda f: f.shift(0.5), lambda s: ("shifted", 0.5, s)),
+        (lambda f: f.select(0, 1), lambda s: ("selected", (0, 1), s)),
+        (lambda f: f.transform(sq), lambda s: ("transformed", sq, s)),
+    ]:
+        f = make(S.GP(S.Matern32().stretch(0.9)))
+        spec = wrap(kspec)
+        approx(f(X, 0.2).logpdf(y), O.fdd_logpdf(spec, X, 0.2, y), rtol=1e-10, atol=0)
+        post = f | (f(X, 0.2), y)
+        mean, var = post(xs).marginals()
+        mo, vo = O.posterior_marginals(spec, X, 0.2, y, xs)
+        approx(mean, np.ravel(mo), atol=1e-8)
+        approx(var, np.ravel(vo), atol=1e-8)
+
+
+def test_shifted_gp_is_correlated_with_its_source(S):
+    """The cross-kernel of ``f.shift(c)`` with ``f`` maps only one argument (``measure.py:286``): check the joint."""
+    x = np.linspace(0, 3, 12)[:, None]
+    c = 0.4
+    m = S.Measure()
+    f = S.GP(S.EQ(), measure=m)
+    g = f.shift(c)
+    y1, y2 = np.sin(x[:, 0]), np.sin(x[:, 0] - c)
+    k = ("eq",)
+    K = np.block([
+        [O.kernel_matrix(k, x), O.kernel_matrix(("shifted2", (None, c), k), x, x)],
+        [O.kernel_matrix(("shifted2", (c, None), k), x, x), O.kernel_matrix(("shifted", c, k), x)],
+    ]) + 0.05 * np.eye(24)
+    want = O.normal_logpdf(np.zeros((24, 1)), K, np.concatenate([y1, y2])[:, None])
+    approx(m.logpdf((f(x, 0.05), y1), (g(x, 0.05), y2)), np.ravel(want)[0], rtol=1e-9, atol=0)
+    # observing f pins down g = f(. - c)
+    post = g | (f(x, 1e-6), y1)
+    approx(post(x[4:8] + c).mean, y1[4:8, None], atol=2e-3)
+
+
+def test_mean_follows_the_input_map(S):
+    f = S.GP(sq, S.EQ())
+    x = np.linspace(-1, 1, 7)
+    approx(f.shift(0.5)(x).mean, (x[:, None] - 0.5) ** 2)
+    approx(f.transform(lambda t: 2 * t)(x).mean, (2 * x[:, None]) ** 2)
+    x2 = RNG.standard_normal((6, 2))
+    f2 = S.GP(lambda t: t.sum(-1, keepdim=True), S.EQ())
+    approx(f2.select(1)(x2).mean, x2[:, 1:2])
+
+
+def test_display_of_mapped_kernels(S):
+    assert str(S.EQ().shift(1.0)) == "EQ() shift 1"
+    assert str(S.EQ().select((0, 2))) == "EQ() : [0, 2]"
+    assert "transform" in str(S.EQ().transform(sq))
