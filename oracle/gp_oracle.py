@@ -109,7 +109,7 @@ def ew_dists(x, y):
 #   ("scaled", c, k)  ("sum", k1, k2)  ("product", k1, k2)  ("stretched", ell, k)
 #   input maps (``GP.shift/select/transform``, ``stheno/model/measure.py:272-345``; the second entry of a pair maps the second
 #   argument, ``None`` = untouched):  ("shifted", c, k)  ("selected", dims, k)  ("transformed", f, k)  and per-argument
-#   ("shifted2", (c1, c2), k)  ("selected2", (dims1, dims2), k)  ("transformed2", (f1, f2), k)  ("stretched2", (l1, l2), k)
+#   ("periodic", period, k)  ("shifted2", (c1, c2), k)  ("selected2", (dims1, dims2), k)  ("transformed2", (f1, f2), k)  ("stretched2", (l1, l2), k)
 # Call sites in the reference: ``stheno/model/fdd.py:66,79``,
 # ``stheno/model/observations.py:139,285,286,304``.
 # --------------------------------------------------------------------------------------
@@ -172,6 +172,15 @@ def _kernel(spec, x, y, d2fn, dfn, same):
             return _uprank(np.asarray(p(a), np.float64))
 
         return _kernel(spec[2], apply(x, p1), apply(y, p2), d2fn, dfn, same and not two)
+    if kind == "periodic":
+        # mlkernels PeriodicKernel [UPSTREAM-RECALLED]: k(u(x), u(y)), u(x) = [sin(2 pi x / p), cos(2 pi x / p)]
+        per = np.asarray(spec[1], np.float64)
+
+        def u(a):
+            a = _uprank(a) * (2 * np.pi) / per
+            return np.concatenate([np.sin(a), np.cos(a)], axis=-1)
+
+        return _kernel(spec[2], u(x), u(y), d2fn, dfn, same)
     raise ValueError(f"unknown kernel {kind!r}")
 
 

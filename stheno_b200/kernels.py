@@ -149,6 +149,12 @@ class Kernel:
         dims = tuple(None if d is None else tuple(np.atleast_1d(d).tolist()) for d in dims)
         return _map_kernel(self, "select", dims)
 
+    def periodic(self, period=1.0):
+        """``k.periodic(p)``: ``k(u(x), u(y))`` with ``u(x) = [sin(2 pi x / p), cos(2 pi x / p)]`` (mlkernels
+        ``PeriodicKernel``; ``README.md`` decomposition example).  An input map like the others: the inner kernel is unchanged."""
+        m = InputMap("periodic", period)
+        return self if isinstance(self, ZeroKernel) else MappedKernel(self, m, m)
+
     def transform(self, *fs):
         """``k.transform(f)``: ``k(f(x), f(y))``; ``k.transform(f1, f2)`` per input, ``None`` = identity (``measure.py:343``).
         ``f`` receives the points as a device tensor ``[..., n, d]`` and returns a tensor (or anything array-like)."""
@@ -175,7 +181,8 @@ class Kernel:
                 return other
             return ProductKernel(self, other)
         if isinstance(other, FunctionType):
-            raise NotImplementedError("function * kernel (TensorProduct) is outside the hot-path scope (SURVEY 8f.3)")
+            # ``f * k``: ``f(x) k(x, y) f(y)`` (mlkernels ``TensorProductKernel(f) * k``, ``stheno/model/measure.py:249``)
+            return self if isinstance(self, ZeroKernel) else FunctionScaledKernel(self, other, other)
         if isinstance(self, ZeroKernel):
             return self
         if not isinstance(other, torch.Tensor) and float(other) == 0.0:
@@ -567,6 +574,10 @@ class InputMap:
             out = t / v.to(device=t.device, dtype=t.dtype)
         elif self.kind == "select":
             out = t[..., list(p)]
+        elif self.kind == "periodic":
+            v = p if isinstance(p, torch.Tensor) else torch.as_tensor(np.asarray(p, np.float64), dtype=t.dtype, device=t.device)
+            ang = t * (2 * np.pi) / v.to(device=t.device, dtype=t.dtype)
+            out = torch.cat([torch.sin(ang), torch.cos(ang)], dim=-1)
         else:
             out = p(t)
             if not isinstance(out, torch.Tensor):
@@ -588,7 +599,7 @@ class InputMap:
         return np.array_equal(np.asarray(a, dtype=object), np.asarray(b, dtype=object))
 
     def render(self):
-        sym = {"shift": "shift", "stretch": ">", "select": ":", "transform": "transform"}[self.kind]
+        sym = {"shift": "shift", "stretch": ">", "select": ":", "transform": "transform", "periodic": "per"}[self.kind]
         if self.kind == "transform":
             return f"{sym} {getattr(self.param, '__name__', 'f')}"
         if self.kind == "select":
@@ -641,7 +652,8 @@ class MappedKernel(Kernel):
 
     @property
     def stationary(self):
-        return self.k.stationary and _same_map(self.m1, self.m2) and self.m1 is not None and self.m1.kind in ("shift", "stretch")
+        return (self.k.stationary and _same_map(self.m1, self.m2) and self.m1 is not None
+                and self.m1.kind in ("shift", "stretch", "periodic"))
 
 
 def _map_kernel(k, kind, params):
@@ -668,6 +680,57 @@ def _map_kernel(k, kind, params):
     if m1 is None and m2 is None:
         return k
     return MappedKernel(k, m1, m2)
+
+
+class FunctionScaledKernel(Kernel):
+    """``g1(x) k(x, y) g2(y)`` for user functions ``g`` (``None`` = 1): ``f * k`` and the one-sided
+    ``TensorProductKernel(f, ones) * k`` of ``GP * function`` (``stheno/model/measure.py:241-251``).  The inner kernel is
+    evaluated by K1; the row / column factors are applied to its dense result."""
+
+    def __init__(self, k, g1, g2):
+        self.k, self.g1, self.g2 = k, g1, g2
+
+    @property
+    def symmetric(self):
+        return self.k.symmetric and self.g1 is self.g2
+
+    def reversed(self):
+        return self if self.symmetric else FunctionScaledKernel(self.k.reversed(), self.g2, self.g1)
+
+    @staticmethod
+    def _factor(g, x):
+        return None if g is None else FunctionMean(g)._dev(x)  # [..., n, 1]
+
+    def _pairwise_dev(self, x, y, same):
+        K = self.k._pairwise_dev(x, y, same)
+        gx, gy = self._factor(self.g1, x), self._factor(self.g2, x if same else y)
+        if gx is not None:
+            K = K * gx
+        if gy is not None:
+            K = K * gy.transpose(-1, -2)
+        return K
+
+    def _elwise_dev(self, x, y, same):
+        k = self.k._elwise_dev(x, y, same)
+        gx, gy = self._factor(self.g1, x), self._factor(self.g2, x if same else y)
+        if gx is not None:
+            k = k * gx
+        if gy is not None:
+            k = k * gy
+        return k
+
+    def _matrix(self, x, y, same):
+        return M.Dense(self._pairwise_dev(x, y, same), x.origin)
+
+    def render(self):
+        n = lambda g: "1" if g is None else getattr(g, "__name__", "f")
+        if self.g1 is self.g2:
+            return f"{n(self.g1)} * {_paren(self.k)}"
+        return f"({n(self.g1)} x {n(self.g2)}) * {_paren(self.k)}"
+
+    @property
+    def stationary(self):
+        return False
 
 
 def _strip_scale(k):

@@ -116,8 +116,10 @@ class GP(RandomProcess):
 
     def __mul__(self, other):
         res = GP()
-        if isinstance(other, GP):
-            raise NotImplementedError("GP * GP (moment matching) is outside the hot-path scope (SURVEY 8f.3)")
+        if isinstance(other, GP):  # moment-matched product (``measure.py:253-270``)
+            for measure in intersection_measure_group(self, other):
+                measure.mul(res, self, other)
+            return res
         for measure in self._measures:
             measure.mul(res, self, other)
         return res

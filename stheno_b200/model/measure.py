@@ -6,7 +6,7 @@ from types import FunctionType
 import numpy as np
 import torch
 
-from ..kernels import ZeroKernel, num_elements
+from ..kernels import FunctionScaledKernel, ZeroKernel, as_input, num_elements
 from ..lazy import LazyMatrix, LazyVector
 from .._util import from_dev
 from .fdd import FDD, _input_meta
@@ -18,6 +18,11 @@ __all__ = ["Measure"]
 
 def _is_numeric(v):
     return isinstance(v, (int, float, np.number, np.ndarray, torch.Tensor))
+
+
+def _left_scaled(k, f):
+    """``TensorProductKernel(f, ones) * k``: ``f(x) k(x, y)`` (``stheno/model/measure.py:250``)."""
+    return k if isinstance(k, ZeroKernel) else FunctionScaledKernel(k, f, None)
 
 
 class Measure:
@@ -121,12 +126,30 @@ class Measure:
         return self._update(p_sum, self.means[p] + other, self.kernels[p], lambda j: self.kernels[p, j])
 
     def mul(self, p_mul, a, b):
-        """``measure.py:218-270`` (scalar multiples; function / GP multiples are out of scope)."""
+        """``measure.py:218-270``: scalar multiples, ``GP * function`` and the moment-matched ``GP * GP``."""
         if not isinstance(a, GP):
             a, b = b, a
         p, other = a, b
-        if isinstance(other, (GP, FunctionType)):
-            raise NotImplementedError("GP * function / GP * GP are outside the hot-path scope (SURVEY 8f.3)")
+        if isinstance(other, GP):
+            p1, p2 = p, other
+            assert_same_measure(p1, p2)
+            m1, m2 = self.means[p1], self.means[p2]
+            mean_fn = lambda m: (lambda x: m._dev(as_input(x)))  # the mean as a plain function of the points
+            term1 = self.sum(GP(), self.mul(GP(), mean_fn(m1), p2), self.mul(GP(), p1, mean_fn(m2)))
+            term2 = self.add_independent_gp(
+                GP(),
+                -(m1 * m2),
+                self.kernels[p1] * self.kernels[p2] + self.kernels[p1, p2] * self.kernels[p2, p1],
+            )
+            return self.sum(p_mul, term1, term2)
+        if isinstance(other, FunctionType):
+            f = other
+            return self._update(
+                p_mul,
+                f * self.means[p],
+                f * self.kernels[p],
+                lambda j: _left_scaled(self.kernels[p, j], f),
+            )
         return self._update(
             p_mul,
             self.means[p] * other,

@@ -254,6 +254,22 @@ class Normal(RandomVector):
         ) / 2
         return self._out(out)
 
+    def w2(self, other):
+        """2-Wasserstein distance to another normal (``stheno/random.py:311-329``).  ``B.root`` (the symmetric PSD square
+        root) comes from a library symmetric eigensolver (``torch.linalg.eigh`` = cuSOLVER): this is off the hot path."""
+
+        def root(a):
+            lam, v = torch.linalg.eigh((a + a.transpose(-1, -2)) / 2)
+            return (v * lam.clamp_min(0).sqrt().unsqueeze(-2)) @ v.transpose(-1, -2)
+
+        a, b = M.dense(self._var_dev()), M.dense(other._var_dev())
+        ra = root(a)
+        r = root(ra @ b @ ra)
+        tr = lambda t: torch.diagonal(t, dim1=-2, dim2=-1).sum(-1)
+        var_part = tr(a) + tr(b) - 2 * tr(r)
+        mean_part = ((self._mean_dev() - other._mean_dev()) ** 2).sum((-1, -2))
+        return self._out(torch.sqrt(torch.clamp(mean_part + var_part, min=0)))
+
     # ---- sampling (SURVEY 8f rank 1) -----------------------------------------------------------------------------
     def sample(self, *args, num=1, noise=None):
         """``sample([state,] num=1, noise=None)`` -> ``(n, num)`` samples ``mean + L eps``

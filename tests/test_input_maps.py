@@ -127,3 +127,82 @@ def test_display_of_mapped_kernels(S):
     assert str(S.EQ().shift(1.0)) == "EQ() shift 1"
     assert str(S.EQ().select((0, 2))) == "EQ() : [0, 2]"
     assert "transform" in str(S.EQ().transform(sq))
+
+
+# ---- GP * function and the moment-matched GP * GP (stheno/model/measure.py:241-270) ---------------------------------
+def gfun(t):
+    return (torch.sin(t) if isinstance(t, torch.Tensor) else np.sin(t)) + 2.0
+
+
+def test_gp_times_function(S):
+    x = np.linspace(0, 3, 14)
+    xs = np.linspace(0.2, 2.8, 5)
+    m = S.Measure()
+    f = S.GP(sq, S.EQ().stretch(0.7), measure=m)
+    h = f * gfun
+    h2 = gfun * f  # either order
+    spec = ("stretched", 0.7, ("eq",))
+    K, gx = O.kernel_matrix(spec, x), np.sin(x) + 2.0
+    approx(S.B.dense(h(x).var), gx[:, None] * K * gx[None, :])
+    approx(S.B.dense(h2(x).var), gx[:, None] * K * gx[None, :])
+    approx(h(x).mean, (gx * x**2)[:, None])
+    approx(h(x).var_diag if hasattr(h(x), "var_diag") else np.diag(S.B.to_numpy(S.B.dense(h(x).var))), gx**2 * np.diag(K))
+    approx(S.B.dense(m.kernels[h, f](x)), gx[:, None] * K)  # only the left argument is scaled
+    approx(S.B.dense(m.kernels[f, h](x)), K * gx[None, :])
+    # log-pdf of the product, and the posterior of h after observing f
+    y = RNG.standard_normal(len(x))
+    want = O.normal_logpdf((gx * x**2)[:, None], gx[:, None] * K * gx[None, :] + 0.1 * np.eye(len(x)), y[:, None])
+    approx(h(x, 0.1).logpdf(y), np.ravel(want)[0], rtol=1e-9, atol=0)
+    yf = np.cos(x)
+    post = h | (f(x, 0.05), yf)
+    Ks = O.kernel_matrix(spec, xs, x)
+    gs = np.sin(xs) + 2.0
+    A = np.linalg.solve(K + 0.05 * np.eye(len(x)) + 1e-12 * np.eye(len(x)), yf - x**2)
+    approx(post(xs).mean, (gs * (xs**2 + Ks @ A))[:, None], atol=1e-8)
+
+
+def test_gp_times_gp_moment_matching(S):
+    x = np.linspace(0, 2, 9)
+    m = S.Measure()
+    f1 = S.GP(sq, S.EQ(), measure=m)
+    f2 = S.GP(lambda t: t + 1.0, S.Matern32().stretch(1.5), measure=m)
+    p = f1 * f2
+    K1 = O.kernel_matrix(("eq",), x)
+    K2 = O.kernel_matrix(("stretched", 1.5, ("matern32",)), x)
+    m1, m2 = x**2, x + 1.0
+    approx(p(x).mean, (m1 * m2)[:, None])
+    approx(S.B.dense(p(x).var), np.outer(m1, m1) * K2 + np.outer(m2, m2) * K1 + K1 * K2)
+    # the product is correlated with its factors: cov(f1 f2, f1) = m2 k1
+    approx(S.B.dense(m.kernels[p, f1](x)), m2[:, None] * K1)
+    approx(S.B.dense(m.kernels[f2, p](x)), K2 * m1[None, :])
+
+
+def test_periodic_kernel(S):
+    x = np.linspace(0, 7, 30)
+    y = np.sin(2 * np.pi * x / 2.5) + 0.05 * RNG.standard_normal(len(x))
+    k = S.EQ().stretch(0.8).periodic(2.5)
+    spec = ("periodic", 2.5, ("stretched", 0.8, ("eq",)))
+    approx(S.B.dense(k(x)), O.kernel_matrix(spec, x))
+    approx(k(x, x + 2.5), O.kernel_matrix(spec, x))  # period 2.5
+    f = S.GP(k)
+    approx(f(x, 0.1).logpdf(y), O.fdd_logpdf(spec, x, 0.1, y), rtol=1e-10, atol=0)
+    assert str(S.EQ().periodic(2.0)) == "EQ() per 2"
+
+
+def test_w2_between_normals(S):
+    rng = np.random.default_rng(3)
+    n = 6
+    A1, A2 = rng.standard_normal((n, n)), rng.standard_normal((n, n))
+    V1, V2 = A1 @ A1.T + 0.5 * np.eye(n), A2 @ A2.T + 0.5 * np.eye(n)
+    m1, m2 = rng.standard_normal((n, 1)), rng.standard_normal((n, 1))
+    d1, d2 = S.Normal(m1, V1), S.Normal(m2, V2)
+
+    def root(a):
+        lam, v = np.linalg.eigh(a)
+        return (v * np.sqrt(np.maximum(lam, 0))) @ v.T
+
+    r1 = root(V1)
+    want = np.sqrt(np.sum((m1 - m2) ** 2) + np.trace(V1) + np.trace(V2) - 2 * np.trace(root(r1 @ V2 @ r1)))
+    approx(d1.w2(d2), want, rtol=1e-8)
+    approx(d1.w2(d1), 0.0, atol=1e-6)
+    approx(d1.w2(d2), d2.w2(d1), rtol=1e-8)
