@@ -206,3 +206,50 @@ def test_w2_between_normals(S):
     approx(d1.w2(d2), want, rtol=1e-8)
     approx(d1.w2(d1), 0.0, atol=1e-6)
     approx(d1.w2(d2), d2.w2(d1), rtol=1e-8)
+
+
+# ---- the reference's own identity tests for these operations (behaviour of tests/model/test_model.py:429-507) ----------
+def assert_equal_normals(S, d1, d2, atol=1e-6):
+    approx(d1.mean, d2.mean, atol=atol, rtol=1e-6)
+    approx(S.B.dense(d1.var), S.B.dense(d2.var), atol=atol, rtol=1e-6)
+
+
+def test_reference_shifting_identities(S):
+    p = S.GP(lambda t: t**2, S.Linear())
+    assert str(p.shift(1)) == "GP(<lambda> shift 1, Linear() shift 1)"
+    p_shifted = p.shift(5)
+    x = np.linspace(0, 5, 10)
+    y = np.asarray(S.B.to_numpy(p_shifted(x).sample())).reshape(-1)
+    post = p.measure | (p_shifted(x, 1e-8), y)
+    assert_equal_normals(S, post(p(x - 5)), post(p_shifted(x)))
+    assert_equal_normals(S, post(p(x)), post(p_shifted(x + 5)))
+
+
+def test_reference_input_transform_identities(S):
+    p = S.GP(lambda t: t**2, S.Linear())
+    assert str(p.transform(lambda t: t)) == "GP(<lambda> transform <lambda>, Linear() transform <lambda>)"
+    root = lambda t: torch.sqrt(t) if isinstance(t, torch.Tensor) else np.sqrt(t)
+    p_t = p.transform(root)
+    x = np.linspace(0.1, 5, 10)
+    y = np.asarray(S.B.to_numpy(p_t(x).sample())).reshape(-1)
+    post = p.measure | (p_t(x, 1e-8), y)
+    assert_equal_normals(S, post(p(np.sqrt(x))), post(p_t(x)))
+    assert_equal_normals(S, post(p(x)), post(p_t(x * x)))
+
+
+def test_reference_selection_identities(S):
+    p = S.GP(lambda t: t**2, S.EQ())
+    assert str(p.select(1)) == "GP(<lambda> : [1], EQ() : [1])"
+    assert str(p.select(1, 2)) == "GP(<lambda> : [1, 2], EQ() : [1, 2])"
+    p2 = p.select(0)  # a GP on 2-D inputs that only looks at the first column
+    x = np.linspace(0, 5, 10)
+    rng = np.random.default_rng(1)
+    x21 = np.stack([x, rng.standard_normal(10)], axis=1)
+    x22 = np.stack([x, rng.standard_normal(10)], axis=1)
+    y = np.asarray(S.B.to_numpy(p2(x21).sample())).reshape(-1)
+    post = p.measure | (p2(x21, 1e-8), y)
+    approx(post(p(x)).mean, y[:, None], atol=1e-4)
+    assert_equal_normals(S, post(p(x)), post(p2(x21)), atol=1e-5)
+    post = p.measure | (p(x, 1e-8), y)
+    approx(post(p2(x22)).mean, y[:, None], atol=1e-4)
+    assert_equal_normals(S, post(p2(x21)), post(p(x)), atol=1e-5)
