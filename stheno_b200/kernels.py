@@ -1089,7 +1089,7 @@ class MappedMean(Mean):
         self.m, self.imap = m, imap
 
     def _dev(self, x):
-        return self.m._dev(self.imap(x))
+        return self.m.dev(self.imap(x))
 
     def render(self):
         return f"{self.m.render()} {self.imap.render()}"

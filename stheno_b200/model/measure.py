@@ -6,7 +6,7 @@ from types import FunctionType
 import numpy as np
 import torch
 
-from ..kernels import FunctionScaledKernel, ZeroKernel, as_input, num_elements
+from ..kernels import FunctionScaledKernel, ZeroKernel, num_elements
 from ..lazy import LazyMatrix, LazyVector
 from .._util import from_dev
 from .fdd import FDD, _input_meta
@@ -134,7 +134,7 @@ class Measure:
             p1, p2 = p, other
             assert_same_measure(p1, p2)
             m1, m2 = self.means[p1], self.means[p2]
-            mean_fn = lambda m: (lambda x: m._dev(as_input(x)))  # the mean as a plain function of the points
+            mean_fn = lambda m: (lambda x: m.dev(x))  # the mean as a plain function of the points
             term1 = self.sum(GP(), self.mul(GP(), mean_fn(m1), p2), self.mul(GP(), p1, mean_fn(m2)))
             term2 = self.add_independent_gp(
                 GP(),

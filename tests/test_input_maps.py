@@ -253,3 +253,27 @@ def test_reference_selection_identities(S):
     post = p.measure | (p(x, 1e-8), y)
     approx(post(p2(x22)).mean, y[:, None], atol=1e-4)
     assert_equal_normals(S, post(p2(x21)), post(p(x)), atol=1e-5)
+
+
+def test_reference_stretching_identities(S):
+    """The cross-kernel of a stretched GP stretches one argument only (``measure.py:305``) -- now a per-argument map."""
+    p = S.GP(lambda t: t**2, S.Linear())
+    p_stretched = p.stretch(5)
+    x = np.linspace(0, 5, 10)
+    y = np.asarray(S.B.to_numpy(p_stretched(x).sample())).reshape(-1)
+    post = p.measure | (p_stretched(x, 1e-8), y)
+    assert_equal_normals(S, post(p(x / 5)), post(p_stretched(x)))
+    assert_equal_normals(S, post(p(x)), post(p_stretched(x * 5)))
+
+
+def test_reference_approximate_multiplication(S):
+    """``tests/model/test_model.py:573-592``: the moment-matched product tracks the product of the sampled factors."""
+    m = S.Measure()
+    p1 = S.GP(20, S.EQ(), measure=m)
+    p2 = S.GP(20, S.EQ(), measure=m)
+    p_prod = p1 * p2
+    x = np.linspace(0, 10, 50)
+    s1, s2 = m.sample(p1(x), p2(x))
+    s1, s2 = np.asarray(S.B.to_numpy(s1)), np.asarray(S.B.to_numpy(s2))
+    post = m | ((p1(x), s1), (p2(x), s2))
+    approx(post(p_prod)(x).mean, s1 * s2, rtol=5e-2, atol=0)
