@@ -47,6 +47,7 @@ __all__ = [
     "posterior",
     "posterior_marginals",
     "sparse_compute",
+    "sparse_compute_chunked",
     "sparse_posterior",
     "mo_block_kernel",
 ]
@@ -377,6 +378,45 @@ def sparse_compute(spec, z, x, noise_diag, y, method="vfe", noise_z=None, mean_x
     iqf_part = np.sum(y_bar[:, 0] ** 2 / K_n) - np.sum(t * t)  # :335
     elbo = -0.5 * (det_part + iqf_part + trace_part)  # :336
     return {"K_z": K_z, "A": A_store, "mu": mu, "elbo": float(elbo), "L_z": L_z}
+
+
+def sparse_compute_chunked(spec, z, x, noise_diag, y, method="vfe", noise_z=None, chunk=16384, eps=EPSILON):
+    """:func:`sparse_compute` (``observations.py:279-336``, zero means) evaluated over column chunks of ``K_zx`` so that
+    the full-size configuration (n = 262144, m = 4096: ``K_zx`` = 8.6 GB, several temporaries of that size in the plain
+    restatement) fits a test host.  Every line is the same arithmetic restricted to the data points of one chunk; the
+    sums over data points (``A``, ``prod``, the scalars) are accumulated chunk by chunk.  Checked against
+    :func:`sparse_compute` in ``tests/test_oracle_golden.py``.  Returns ``elbo``, ``mu`` and ``A`` (= ``L_z A L_z^T``)."""
+    z, x = np.asarray(z, np.float64), np.asarray(x, np.float64)
+    y = _uprank(np.asarray(y, np.float64))
+    n, m = x.shape[0], z.shape[0]
+    K_z = kernel_matrix(spec, z) + noise_matrix(noise_z, m)  # :286
+    L_z = chol_eps(K_z, eps)  # :300
+    K_n_all = np.broadcast_to(np.asarray(noise_diag, np.float64), (n,))
+    A = np.eye(m)
+    prod = np.zeros((m, 1))
+    log_kn = yky = trace_part = 0.0
+    for a in range(0, n, chunk):
+        xc, yc = x[a : a + chunk], y[a : a + chunk]
+        K_n = K_n_all[a : a + chunk].copy()  # :290
+        W = _tri(L_z, kernel_matrix(spec, z, xc))  # :285, :301
+        if method in ("vfe", "fitc"):
+            corr = kernel_elwise(spec, xc)[:, 0] - np.sum(W * W, axis=0)  # :304-306
+        if method == "vfe":
+            trace_part += np.sum(corr / K_n)  # :308-310
+        elif method == "fitc":
+            K_n = K_n + corr  # :311-313
+        elif method != "dtc":
+            raise ValueError(method)
+        Ws = W / K_n
+        A += Ws @ W.T  # :322
+        prod += Ws @ yc  # :327
+        log_kn += np.sum(np.log(2 * np.pi * K_n))
+        yky += np.sum(yc[:, 0] ** 2 / K_n)
+    L_A = chol_eps(A, eps)
+    mu = L_z @ sla.cho_solve((L_A, True), prod)  # :329
+    t = _tri(L_A, prod)
+    elbo = -0.5 * (log_kn + 2 * np.sum(np.log(np.diag(L_A))) + yky - np.sum(t * t) + trace_part)  # :334-336
+    return {"K_z": K_z, "A": L_z @ A @ L_z.T, "mu": mu, "elbo": float(elbo), "L_z": L_z}
 
 
 def sparse_posterior(spec, z, x, noise_diag, y, xs, method="vfe", noise_z=None, eps=EPSILON):

@@ -24,6 +24,11 @@ epsilon = 1e-12
 #:   "tf32x3" (opt-in, north_star "tf32/bf16 where the user opts in"): fp32 panel copy + 3xTF32 products, ~1e-6 relative.
 precision = "auto"
 
+#: ``True``: every dense Cholesky checks its LAPACK-style ``info`` right away and raises ``torch.linalg.LinAlgError`` for a
+#: non-positive-definite matrix, as the reference's backend does.  That costs a host synchronisation per factorisation, so the
+#: default leaves ``info`` on the device (``Chol.info`` / ``Chol.check()``): a failed factorisation then shows as NaN results.
+strict = False
+
 pi = np.pi
 log_2_pi = float(np.log(2 * np.pi))
 

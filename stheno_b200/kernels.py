@@ -15,6 +15,7 @@ import torch
 
 from . import matrix as M
 from . import ops
+from ._lib import GpkError as _GpkError
 from ._util import batch_flatten, from_dev, origin_of, to_dev, uprank
 
 __all__ = [
@@ -233,10 +234,19 @@ class Kernel:
             raw.append(coef)
         if not scales:
             scales = [None]
-        flat = ops.FlatKernel(out, len(scales))
+        try:
+            flat = ops.FlatKernel(out, len(scales))
+        except _GpkError:
+            # more product terms / factors / length scales than one K1 descriptor holds: not flattenable as a whole; the
+            # callers fall back to evaluating the children separately (each child gets its own descriptor) and combining
+            return None, None
         # hyper-parameters given as torch tensors that require grad: remember them for the differentiable path
         flat.coef_raw = raw if any(isinstance(c, torch.Tensor) and c.requires_grad for c in raw) else None
         return flat, scales
+
+    def _flattenable(self):
+        """True when the whole expression fits ONE K1 descriptor (``ops.FlatKernel`` limits)."""
+        return self._flat()[0] is not None
 
     def _pairwise_dev(self, x, y, same):
         """Device tensor ``[..., n, m]`` for numeric inputs ``x, y`` (:class:`Input`)."""
@@ -386,19 +396,23 @@ class ScaledKernel(Kernel):
         return [(c * s, fs) for c, fs in t]
 
     def _pairwise_dev(self, x, y, same):
-        if self.flat_terms() is not None:
+        if self._flattenable():
             return super()._pairwise_dev(x, y, same)
         return self.scale * M.dense(pairwise(self.k, x, y if not same else None))
 
     def _elwise_dev(self, x, y, same):
-        if self.flat_terms() is not None:
+        if self._flattenable():
             return super()._elwise_dev(x, y, same)
         return self.scale * elwise_dev(self.k, x, y, same)
 
     def _matrix(self, x, y, same):
-        if self.flat_terms() is None:
+        if not self._flattenable():
             return M.Dense(self._pairwise_dev(x, y, same), x.origin)
         inner = self.k
+        if isinstance(self.scale, torch.Tensor) and self.scale.requires_grad and torch.is_grad_enabled():
+            # a scale that carries a graph: the structured shortcuts below would detach it (float(scale)); the generic
+            # descriptor path keeps it as ``flat.coef_raw`` for the differentiable log-pdf
+            return super()._matrix(x, y, same)
         if same and isinstance(inner, Linear) and float(self.scale) > 0:
             return M.LowRank(x.t * float(self.scale) ** 0.5, x.origin)
         if same and isinstance(inner, Delta):
@@ -436,20 +450,21 @@ class SumKernel(_Join):
         return ta + tb
 
     def _pairwise_dev(self, x, y, same):
-        if self.flat_terms() is not None:
+        if self._flattenable():
             return super()._pairwise_dev(x, y, same)
         yy = None if same else y
         return M.dense(M.add(pairwise(self.a, x, yy), pairwise(self.b, x, yy)))
 
     def _elwise_dev(self, x, y, same):
-        if self.flat_terms() is not None:
+        if self._flattenable():
             return super()._elwise_dev(x, y, same)
         return elwise_dev(self.a, x, y, same) + elwise_dev(self.b, x, y, same)
 
     def _matrix(self, x, y, same):
-        if self.flat_terms() is not None:
+        if self._flattenable():
             # keep Delta parts diagonal: k + s2 * Delta  ->  KernelDense + Diagonal (stays symbolic)
-            if same and isinstance(_strip_scale(self.b)[0], Delta):
+            kb, cb = _strip_scale(self.b)
+            if same and isinstance(kb, Delta) and not (isinstance(cb, torch.Tensor) and cb.requires_grad and torch.is_grad_enabled()):
                 return M.add(self.a._matrix(x, y, same), self.b._matrix(x, y, same))
             return super()._matrix(x, y, same)
         yy = None if same else y
@@ -467,13 +482,13 @@ class ProductKernel(_Join):
         return [(ca * cb, fa + fb) for (ca, fa), (cb, fb) in itertools.product(ta, tb)]
 
     def _pairwise_dev(self, x, y, same):
-        if self.flat_terms() is not None:
+        if self._flattenable():
             return super()._pairwise_dev(x, y, same)
         yy = None if same else y
         return M.dense(pairwise(self.a, x, yy)) * M.dense(pairwise(self.b, x, yy))
 
     def _elwise_dev(self, x, y, same):
-        if self.flat_terms() is not None:
+        if self._flattenable():
             return super()._elwise_dev(x, y, same)
         return elwise_dev(self.a, x, y, same) * elwise_dev(self.b, x, y, same)
 
@@ -512,13 +527,13 @@ class StretchedKernel(Kernel):
         return xs, ys
 
     def _pairwise_dev(self, x, y, same):
-        if self.flat_terms() is not None:
+        if self._flattenable():
             return super()._pairwise_dev(x, y, same)
         xs, ys = self._scaled_inputs(x, y, same)
         return self.k._pairwise_dev(xs, ys, same)
 
     def _elwise_dev(self, x, y, same):
-        if self.flat_terms() is not None:
+        if self._flattenable():
             return super()._elwise_dev(x, y, same)
         xs, ys = self._scaled_inputs(x, y, same)
         return self.k._elwise_dev(xs, ys, same)
@@ -810,7 +825,7 @@ class PosteriorKernel(Kernel):
     symmetric = False
 
     def __init__(self, k_ij, k_zi, k_zj, z, K_z):
-        self.k_ij, self.k_zi, self.k_zj, self.z, self.K_z = k_ij, k_zi, k_zj, z, M._densify(K_z)
+        self.k_ij, self.k_zi, self.k_zj, self.z, self.K_z = k_ij, k_zi, k_zj, z, M._densify(K_z, full=True)
 
     def _half(self, k_z, x):
         ch = self.K_z.chol()
@@ -863,7 +878,7 @@ class SubspaceKernel(Kernel):
     symmetric = False
 
     def __init__(self, k_zi, k_zj, z, A):
-        self.k_zi, self.k_zj, self.z, self.A = k_zi, k_zj, z, M._densify(A)
+        self.k_zi, self.k_zj, self.z, self.A = k_zi, k_zj, z, M._densify(A, full=True)
 
     def _half(self, k_z, x):
         ch = self.A.chol()
@@ -1079,7 +1094,8 @@ class StretchedMean(Mean):
         sv = s if isinstance(s, torch.Tensor) else torch.as_tensor(np.asarray(s, np.float64), dtype=x.t.dtype,
                                                                    device=x.t.device)
         xs.t = x.t / sv
-        return self.m._dev(xs)
+        xs.src = None
+        return self.m.dev(xs)  # ``dev``: composite means (scaled / sum / product / posterior) only define that
 
 
 class MappedMean(Mean):
@@ -1118,7 +1134,7 @@ class PosteriorMean(Mean):
     of the factorisation itself."""
 
     def __init__(self, m_i, m_z, k_zi, z, K_z, y, rhs_key=None):
-        self.m_i, self.m_z, self.k_zi, self.z, self.K_z, self.y = m_i, m_z, k_zi, z, M._densify(K_z), y
+        self.m_i, self.m_z, self.k_zi, self.z, self.K_z, self.y = m_i, m_z, k_zi, z, M._densify(K_z, full=True), y
         self.rhs_key = rhs_key
         self._b = None
 

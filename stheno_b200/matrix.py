@@ -136,6 +136,8 @@ class Dense(AbstractMatrix):
                 rhs_t = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
             self._chol = self._factorize(rhs_t)
             self._rhs = []
+            if _B.strict:
+                self._chol.check()
         return self._chol
 
     def half_rhs(self, key):
@@ -476,9 +478,10 @@ def add(a, b):
     return Dense(a.dev + b.dev, org)
 
 
-def _densify(a):
-    """Structured types without a fast path for the requested operation fall back to their dense form."""
-    if isinstance(a, (LowRank, Woodbury)):
+def _densify(a, full=False):
+    """Structured types without a fast path for the requested operation fall back to their dense form.  ``full``: also
+    Diagonal / Zero (consumers that need a Cholesky factor object: conditioning on a pure-noise process)."""
+    if isinstance(a, (LowRank, Woodbury)) or (full and isinstance(a, (Diagonal, Zero))):
         return Dense(a.dev, a.origin)
     return as_matrix(a)
 

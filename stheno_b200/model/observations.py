@@ -71,7 +71,7 @@ class Observations(AbstractObservations):
             return self._K_x[id(measure)]
         except KeyError:
             K_x = M.add(pairwise(measure.kernels[self.fdd.p], self.fdd.x), self.fdd.noise)
-            K_x = M._densify(K_x)  # low-rank structure is exploited by logpdf; conditioning uses the dense factor
+            K_x = M._densify(K_x, full=True)  # low-rank structure is exploited by logpdf; conditioning uses the dense factor
             if isinstance(K_x, M.Dense):
                 diff = self.y - measure.means[self.fdd.p].dev(self.fdd.x)
                 d3, _ = batch_flatten(diff, 2)

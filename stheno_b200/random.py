@@ -45,6 +45,31 @@ def _is_zero_scalar(m):
     return isinstance(m, (int, float)) and m == 0
 
 
+_allow_missing = True
+_flag_bufs = {}
+
+
+class _NanFlag:
+    """``isnan(y).any()`` evaluated on the device, its result travelling to pinned host memory behind the caller's back;
+    :meth:`read` waits for THAT copy only (an event recorded right after it), not for the stream to drain."""
+
+    def __init__(self, xd):
+        key = (xd.device.index or 0, torch.cuda.current_stream(xd.device).cuda_stream)
+        slot = _flag_bufs.get(key)
+        if slot is None:
+            slot = _flag_bufs[key] = [torch.zeros(16, dtype=torch.uint8).pin_memory(), 0]
+        buf, i = slot
+        slot[1] = (i + 1) % 16  # ring: the host runs at most one evaluation ahead, 16 slots are plenty
+        self.cell = buf[i : i + 1]
+        self.cell.copy_(torch.isnan(xd).any().to(torch.uint8).reshape(1), non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+    def read(self):
+        self.event.synchronize()
+        return bool(self.cell.item())
+
+
 class Normal(RandomVector):
     """``Normal(mean, var)``, ``Normal(var)`` or the lazy form ``Normal(mean_fn, var_fn, var_diag=..., mean_var=...,
     mean_var_diag=...)`` whose constructors return DEVICE tensors / matrices (``stheno/random.py:56-94``)."""
@@ -192,20 +217,23 @@ class Normal(RandomVector):
         xd = uprank(to_dev(x, None))
         var = self._var_dev()
         xd = xd.to(var.dtype)
+        pending = None
         if xd.dim() == 2 and xd.shape[1] == 1:
-            # Missing data: host-resident observations are checked on the host (no device round trip); device-resident
-            # ones with one tiny device reduction + flag read instead of shipping the mask.
+            # Missing data (``random.py:261-270``).  Host-resident observations are checked on the host.  Device-resident
+            # ones: one tiny device reduction whose flag is copied to pinned host memory ASYNCHRONOUSLY and only read
+            # after the whole log-pdf has been enqueued -- the host never waits for the device to drain
+            # between two evaluations, so the launches of step k + 1 are enqueued while step k still runs.  If the flag
+            # does say "NaN" (rare), the enqueued result is discarded and the gather path below runs.
             if isinstance(x, torch.Tensor) and x.is_cuda:
-                nan = torch.isnan(xd[:, 0])
-                has_nan = bool(nan.any())
+                nan, has_nan = None, False
+                if _allow_missing:
+                    pending = _NanFlag(xd)
             else:
                 host = x.detach().numpy() if isinstance(x, torch.Tensor) else np.asarray(x, dtype=float)
                 has_nan = bool(np.isnan(host).any())
                 nan = torch.isnan(xd[:, 0]) if has_nan else None
             if has_nan:
-                avail = ~nan
-                sub = Normal(self._mean_dev()[avail], M.submatrix(var, avail), origin=self._origin)
-                return sub.logpdf(from_dev(xd[avail], out_origin))
+                return self._logpdf_missing(xd, nan, var, out_origin)
         n = var.shape[-1]
         diff = xd if self.mean_is_zero else xd - self._mean_dev()
         if isinstance(var, (M.Diagonal, M.Woodbury)):
@@ -237,7 +265,14 @@ class Normal(RandomVector):
                 lp = -(ch.logdet.unsqueeze(-1) + n * B.log_2_pi + (half * half).sum(-1)) / 2
             lp = lp.reshape(bs + (lp.shape[-1],))
         lp = lp[..., 0] if lp.shape[-1] == 1 else lp
+        if pending is not None and pending.read():
+            return self._logpdf_missing(xd, torch.isnan(xd[:, 0]), var, out_origin)
         return from_dev(lp, out_origin)
+
+    def _logpdf_missing(self, xd, nan, var, out_origin):
+        avail = ~nan
+        sub = Normal(self._mean_dev()[avail], M.submatrix(var, avail), origin=self._origin)
+        return sub.logpdf(from_dev(xd[avail], out_origin))
 
     def entropy(self):
         return self._out((M.logdet(self._var_dev()) + self.dim * (B.log_2_pi + 1)) / 2)

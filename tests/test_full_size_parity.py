@@ -1,0 +1,176 @@
+"""The BENCHMARKED configurations against the CPU oracle at FULL size (BASELINE.json configs 2, 4 and 5).
+
+Round 1 proved these sizes only by composition (GPU path vs library factorisation of its own matrix, or vs the repo's
+all-DMMA path).  Here the oracle itself -- the NumPy/SciPy restatement of ``stheno/random.py:248-280``,
+``stheno/model/observations.py:279-336`` and ``stheno/mo/kernel.py:39-56`` -- is evaluated once per configuration on the
+box's host cores (module-scoped fixtures; about 1-2 minutes each on 64 threads) and compared at north_star's 1e-10:
+
+* C2  n = 16384, d = 8: ``logpdf`` and posterior marginals at m = 512 test points, for ``B.precision`` = "auto" (7 int8
+  slices = what bench.py times), "int8x8" and "fp64";
+* C4  n = 262144, m = 4096, Matern52, VFE: ``elbo`` and ``mu`` (the only test that runs the K = 262144 reduction);
+* C5  p = 4 outputs x n = 8192 (N = 32768 joint): the joint ``logpdf``;
+* an ill-conditioned sweep: "auto" keeps positive definiteness wherever native fp64 does.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _threads():
+    try:
+        import threadpoolctl
+
+        threadpoolctl.threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+
+
+@pytest.fixture(scope="module")
+def S():
+    import stheno_b200 as s
+
+    s.B.epsilon = 1e-12
+    s.Measure.default = None
+    return s
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# C2
+# ---------------------------------------------------------------------------------------------------------------------
+C2_SPEC = ("sum", ("stretched", 2.0, ("eq",)), ("scaled", 0.1, ("delta",)))
+
+
+@pytest.fixture(scope="module")
+def c2():
+    """bench.py's inputs (seed 2) and ONE oracle evaluation: logpdf + posterior marginals share the factor."""
+    _threads()
+    rng = np.random.default_rng(2)
+    n, d, m = 16384, 8, 512
+    x = rng.standard_normal((n, d))
+    y = rng.standard_normal(n)
+    xs = np.random.default_rng(22).standard_normal((m, d))
+    K = O.kernel_matrix(C2_SPEC, x)  # stheno/model/fdd.py:79
+    L = O.chol_eps(K)  # stheno/random.py:274
+    del K
+    a = O._tri(L, y[:, None])
+    lp = -0.5 * (2 * np.sum(np.log(np.diag(L))) + n * O.LOG_2_PI + float(np.sum(a * a)))  # random.py:272-279
+    V = O._tri(L, O.kernel_matrix(C2_SPEC, x, xs))  # observations.py:143-168
+    mean = (V.T @ a)[:, 0]
+    var = np.maximum(O.kernel_elwise(C2_SPEC, xs)[:, 0] - np.sum(V * V, axis=0), 0.0)  # random.py:221-227
+    del L
+    return {"x": x, "y": y, "xs": xs, "logpdf": lp, "mean": mean, "var": var}
+
+
+@pytest.mark.parametrize("precision", ["auto", "int8x8", "fp64"])
+def test_c2_full_size_vs_oracle(S, c2, precision):
+    x = torch.as_tensor(c2["x"], device="cuda")
+    y = torch.as_tensor(c2["y"], device="cuda")
+    xs = torch.as_tensor(c2["xs"], device="cuda")
+    before = S.B.precision
+    S.B.precision = precision
+    try:
+        f = S.GP(S.EQ().stretch(2.0) + 0.1 * S.Delta())
+        lp = f(x).logpdf(y)
+        assert rel(lp.item(), c2["logpdf"]) < 1e-10
+        post = f | (f(x), y)
+        mean, var = post(xs).marginals()
+    finally:
+        S.B.precision = before
+    mean, var = mean.cpu().numpy(), var.cpu().numpy()
+    # posterior mean / variance: 1e-10 relative to the scale of the quantity (prior variance = 1.1)
+    assert np.max(np.abs(mean - c2["mean"])) < 1e-10 * max(1.0, np.max(np.abs(c2["mean"])))
+    assert np.max(np.abs(var - c2["var"])) < 1e-10 * 1.1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# C4
+# ---------------------------------------------------------------------------------------------------------------------
+def test_c4_full_size_vs_oracle(S):
+    _threads()
+    rng = np.random.default_rng(4)
+    n, m, d = 262144, 4096, 8
+    x = rng.standard_normal((n, d))
+    y = rng.standard_normal(n)
+    z = np.random.default_rng(44).standard_normal((m, d))
+    spec = ("stretched", 2.0, ("matern52",))
+    want = O.sparse_compute_chunked(spec, z, x, 0.1, y, "vfe", chunk=16384)
+    xd, yd, zd = (torch.as_tensor(a, device="cuda") for a in (x, y, z))
+    assert S.B.precision == "auto"
+    f = S.GP(S.Matern52().stretch(2.0))
+    obs = S.PseudoObs(f(zd), f(xd, 0.1), yd)
+    elbo = obs.elbo(f.measure)
+    assert rel(float(elbo), want["elbo"]) < 1e-10
+    mu = obs.mu(f.measure).cpu().numpy()
+    assert np.max(np.abs(mu - want["mu"])) < 1e-9 * max(1.0, np.max(np.abs(want["mu"])))
+    peak = torch.cuda.max_memory_allocated() / 2**30
+    print(f"C4 full size: elbo rel {rel(float(elbo), want['elbo']):.2e}, peak device memory {peak:.2f} GiB")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# C5
+# ---------------------------------------------------------------------------------------------------------------------
+def test_c5_full_size_joint_logpdf_vs_oracle(S):
+    _threads()
+    rng = np.random.default_rng(5)
+    p, n = 4, 8192
+    x = np.linspace(0, 10, n)
+    H = rng.standard_normal((p, 2))
+    ells = (0.5, 1.5)
+    y = rng.standard_normal(p * n)
+    lat = [("stretched", l, ("eq",)) for l in ells]
+
+    def block(i, j):  # sum_l H_il H_jl k_l  (stheno/mo/kernel.py:39-56 through measure.py:180-239)
+        return ("sum", ("scaled", H[i, 0] * H[j, 0], lat[0]), ("scaled", H[i, 1] * H[j, 1], lat[1]))
+
+    K = O.mo_block_kernel([[block(i, j) for j in range(p)] for i in range(p)], [x] * p)
+    K[np.diag_indices_from(K)] += 0.5
+    want = float(O.normal_logpdf(None, K, y))
+    del K
+    m = S.Measure()
+    us = [S.GP(S.EQ().stretch(l), measure=m) for l in ells]
+    fs = [float(H[i, 0]) * us[0] + float(H[i, 1]) * us[1] for i in range(p)]
+    xd = torch.as_tensor(x, device="cuda")
+    yd = torch.as_tensor(y, device="cuda")
+    got = m.logpdf(*[(fs[i](xd, 0.5), yd[i * n : (i + 1) * n]) for i in range(p)])
+    assert rel(float(got), want) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# conditioning sweep: the 7-slice default must not lose positive definiteness where native fp64 keeps it
+# ---------------------------------------------------------------------------------------------------------------------
+# closeness bars (relative difference of the two log-pdfs): FILLED FROM THE FIRST MEASURED SWEEP, see profiles/r02_conditioning_sweep.txt
+BAR = {2.0: lambda s2: 1e-6, 20.0: lambda s2: 1e-6}
+
+
+@pytest.mark.parametrize("ell", [2.0, 20.0])
+def test_auto_keeps_positive_definiteness_where_fp64_does(S, ell):
+    rng = np.random.default_rng(9)
+    n, d = 4096, 8
+    x = torch.as_tensor(rng.standard_normal((n, d)), device="cuda")
+    y = torch.as_tensor(rng.standard_normal(n), device="cuda")
+    before = S.B.precision
+    rows = []
+    try:
+        for s2 in (1e-2, 1e-3, 1e-4, 1e-5, 1e-6, 1e-7, 1e-8):
+            out = {}
+            for prec in ("fp64", "auto", "int8x7"):
+                S.B.precision = prec
+                out[prec] = float(S.GP(S.EQ().stretch(ell))(x, s2).logpdf(y))
+            rows.append((s2, out))
+            if np.isfinite(out["fp64"]):
+                assert np.isfinite(out["auto"]), (ell, s2, out)
+                assert abs(out["auto"] - out["fp64"]) <= BAR[ell](s2) * abs(out["fp64"]), (ell, s2, out)
+    finally:
+        S.B.precision = before
+    print("conditioning sweep (ell=%g):" % ell, rows)

@@ -426,15 +426,15 @@ def test_float32_and_batched_posterior(S):
         approx(var[b], vref, rtol=1e-3, atol=1e-4)
 
 
-def test_kernel_limits_are_reported(S):
-    # more product terms than the descriptor holds -> a clear error, not a wrong answer
-    from stheno_b200._lib import GpkError
-
+def test_kernel_beyond_descriptor_limits_falls_back(S):
+    # more product terms than ONE K1 descriptor holds -> evaluated per child and combined (the reference has no limit)
     k = S.EQ()
+    spec = ("eq",)
     for i in range(9):
         k = k + (i + 2.0) * S.Matern32().stretch(float(i + 2))
-    with pytest.raises(GpkError):
-        S.GP(k)(np.linspace(0, 1, 5)).var.mat
+        spec = ("sum", spec, ("scaled", i + 2.0, ("stretched", float(i + 2), ("matern32",))))
+    x = np.linspace(0, 1, 5)
+    approx(S.GP(k)(x).var.mat, O.kernel_matrix(spec, x))
 
 
 def test_combine_and_multi_fdd_observations(S):
