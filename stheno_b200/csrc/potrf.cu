@@ -143,6 +143,178 @@ potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int64_t a_bs, T* __restrict__ 
   }
 }
 
+// ---- recursive leaf Cholesky: the 128 x 128 block as 4 x 4 sub-blocks of 32 x 32 in shared memory ---------------------
+// The flat kernel above walks 128 dependent column steps of ~360 ns each (STS -> CTA barrier -> 16 LDS -> rsqrt -> 16 DMUL ->
+// up to 64 DFMA per thread): 46 us per block, all of it on the factorisation's critical path.  Here the
+// dependent chain per column is the one a single WARP needs -- shuffle of the pivot, rsqrt, one multiply, a warp-level
+// broadcast of the column through shared memory, one DFMA on the next column -- and everything that is not on the chain
+// (the triangular solves of the rows below a 32-block and the rank-32 updates of the blocks to its right) runs on the
+// other warps, the part the next 32-block does not need even concurrently with that block's factorisation:
+//   for b = 0..3:   S0  warp 0: potf2 of A_bb in registers (lane = row)      | warps 1..15: rest of the rank-32 update of step b-1
+//                   S1  one thread per row below: x L_bb^T = a  (forward substitution in registers, L_bb^T broadcast)
+//                   S2  all warps: rank-32 update of block column b+1 only (what S0 / S1 of the next step read)
+// Arithmetic is fp64 whatever the storage type (fp32 problems: the leaf is < 2 % of the flops).
+constexpr int RL_THREADS = 384;  // 12 warps: 170 registers per thread keep the 32-column factorisation of S0 out of local memory
+constexpr int RL_WARPS = RL_THREADS / 32;
+constexpr int RL_LD = NB + 2;  // even: rows stay 16-byte aligned for the broadcast LDS.128 of the update
+constexpr int RL_SMEM = (NB * RL_LD + 32 * 32 + 32) * (int)sizeof(double);
+
+// rank-32 update of the 32 x 32 block (r, c) with block column b:  A_rc[:, j0:j1) -= X_r X_c[j0:j1)^T ; lane = row of the block
+__device__ __forceinline__ void rl_update_cols(double* S, int r, int c, int b, int j0, int j1, int lane) {
+  const double* xr = S + (32 * r + lane) * RL_LD + 32 * b;
+  double x[32];
+#pragma unroll
+  for (int k = 0; k < 32; k += 2) {
+    const double2 v = *reinterpret_cast<const double2*>(xr + k);
+    x[k] = v.x;
+    x[k + 1] = v.y;
+  }
+  for (int j = j0; j < j1; ++j) {
+    if (r == c && j > lane) break;  // diagonal block: only the lower triangle is ever read again (warp-uniform bound below)
+    const double* xc = S + (32 * c + j) * RL_LD + 32 * b;  // same address in every lane: broadcast
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 32; k += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(xc + k);
+      s0 = fma(x[k], v.x, s0);
+      s1 = fma(x[k + 1], v.y, s1);
+    }
+    double* o = S + (32 * r + lane) * RL_LD + 32 * c + j;
+    *o -= s0 + s1;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RL_THREADS, 1)
+potrf_leaf_rec_kernel(T* __restrict__ A, int64_t lda, int64_t a_bs, T* __restrict__ logdet, int32_t* __restrict__ info,
+                      int32_t pivot_base) {
+  extern __shared__ __align__(16) unsigned char rl_smem[];
+  double* S = reinterpret_cast<double*>(rl_smem);  // [128][RL_LD]
+  double* colT = S + NB * RL_LD;                   // [32][32]: colT[j][i] = L_bb[i][j] (column j of the current diagonal block)
+  double* dinv = colT + 32 * 32;                   // [32]: 1 / L_bb[j][j]
+  const int bidx = blockIdx.x;
+  A += (int64_t)bidx * a_bs;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- load the lower triangle (granules of two columns; the granule that straddles the diagonal is loaded whole)
+  for (int gi = tid; gi < NB * NB / 2; gi += RL_THREADS) {
+    const int row = gi >> 6, k = (gi & 63) * 2;
+    if (k <= row) {
+      const T* src = A + (int64_t)row * lda + k;
+      double2 v;
+      if (sizeof(T) == 8) {
+        v = *reinterpret_cast<const double2*>(src);
+      } else {
+        const float2 f = *reinterpret_cast<const float2*>(src);
+        v = make_double2((double)f.x, (double)f.y);
+      }
+      *reinterpret_cast<double2*>(S + row * RL_LD + k) = v;
+    }
+  }
+  __syncthreads();
+
+  double logsum = 0.0;  // warp 0 only
+#pragma unroll 1
+  for (int b = 0; b < 4; ++b) {
+    // ---- S0: warp 0 factorises A_bb; the other warps finish the rank-32 update of step b - 1 (blocks right of column b)
+    if (warp == 0) {
+      double a[32];
+      double diag_l = 1.0;
+      const double* row = S + (32 * b + lane) * RL_LD + 32 * b;
+#pragma unroll
+      for (int k = 0; k < 32; k += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(row + k);
+        a[k] = v.x;
+        a[k + 1] = v.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const double d = __shfl_sync(0xffffffffu, a[j], j);
+        if (lane == 0 && !(d > 0.0)) atomicCAS(info + bidx, 0, pivot_base + 32 * b + j + 1);
+        const double inv = rsqrt(d);
+        const double l = a[j] * inv;  // lane j: sqrt(d); lanes > j: L[lane][j]; lanes < j: unused
+        colT[j * 32 + lane] = l;
+        if (lane == j) {
+          dinv[j] = inv;
+          diag_l = l;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = j + 1; k < 32; ++k) a[k] = fma(-l, colT[j * 32 + k], a[k]);
+        a[j] = l;
+      }
+      double* out = S + (32 * b + lane) * RL_LD + 32 * b;
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k <= lane) out[k] = a[k];
+      logsum += log(diag_l);
+    } else if (b > 0) {
+      // blocks (r, c), b + 1 <= c <= r <= 3, updated with block column b - 1: units of 4 columns over warps 1..RL_WARPS-1
+      const int pb = b - 1;
+      const int nblk = (4 - b) * (3 - b) / 2;  // b = 1: (2,2) (3,2) (3,3) ; b = 2: (3,3) ; b = 3: none
+      for (int u = warp - 1; u < nblk * 8; u += RL_WARPS - 1) {
+        const int blk = u >> 3, q = u & 7;
+        int r, c;
+        if (b == 1) {
+          c = (blk == 2) ? 3 : 2;
+          r = (blk == 0) ? 2 : 3;
+        } else {
+          r = c = 3;
+        }
+        rl_update_cols(S, r, c, pb, 4 * q, 4 * q + 4, lane);
+      }
+    }
+    __syncthreads();
+    if (b == 3) break;
+    // ---- S1: rows below the diagonal block: x L_bb^T = a, one thread per row
+    const int nrows = NB - 32 * (b + 1);
+    if (tid < nrows) {
+      double* rowp = S + (32 * (b + 1) + tid) * RL_LD + 32 * b;
+      double x[32];
+#pragma unroll
+      for (int k = 0; k < 32; k += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(rowp + k);
+        x[k] = v.x;
+        x[k + 1] = v.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        x[j] *= dinv[j];
+#pragma unroll
+        for (int k = j + 1; k < 32; ++k) x[k] = fma(-x[j], colT[j * 32 + k], x[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 32; k += 2) *reinterpret_cast<double2*>(rowp + k) = make_double2(x[k], x[k + 1]);
+    }
+    __syncthreads();
+    // ---- S2: rank-32 update of block column b + 1 (blocks (r, b + 1), r = b + 1..3), units of 2 columns over all warps
+    {
+      const int c = b + 1;
+      for (int u = warp; u < (4 - c) * 16; u += RL_WARPS) rl_update_cols(S, c + (u >> 4), c, b, 2 * (u & 15), 2 * (u & 15) + 2, lane);
+    }
+    __syncthreads();
+  }
+
+  // ---- store the lower triangle
+  for (int gi = tid; gi < NB * NB / 2; gi += RL_THREADS) {
+    const int row = gi >> 6, k = (gi & 63) * 2;
+    if (k <= row) {
+      const double2 v = *reinterpret_cast<const double2*>(S + row * RL_LD + k);
+      T* dst = A + (int64_t)row * lda + k;
+      if (k + 1 <= row) {
+        if (sizeof(T) == 8) *reinterpret_cast<double2*>(dst) = v;
+        else *reinterpret_cast<float2*>(dst) = make_float2((float)v.x, (float)v.y);
+      } else {
+        dst[0] = (T)v.x;  // diagonal element at an even column: the element right of it belongs to the upper triangle
+      }
+    }
+  }
+  if (logdet != nullptr && warp == 0) {
+    const double s = warp_sum(logsum);
+    if (lane == 0) atomicAdd(logdet + bidx, (T)(2.0 * s));
+  }
+}
+
 // ---- leaf TRSM:  X L^T = B  (B: rows x 128, 64 rows per CTA), in place ----------------------------------------
 // thread (r, cg) = (tid % 64, tid / 64) owns row r, columns 32 cg .. 32 cg + 31 in registers.
 // UPPER == true solves X L = B instead (backward substitution; L still lower-triangular).
@@ -462,7 +634,18 @@ static int launch_potrf_leaf(T* A, int64_t lda, int64_t a_bs, T* logdet, int32_t
   //  retire the 16 x 16 step's dependent instruction stream fast enough.
   //  A two-columns-per-barrier (rank-2) variant measured the same: the leaf is bound by its dependent
   //  STS -> barrier -> LDS -> rsqrt -> DMUL -> DFMA chain, not by the barrier count or the fp64 pipe.)
-  potrf_leaf_kernel<T><<<batch, 256, 0, stream>>>(A, lda, a_bs, logdet, info, pivot_base);
+  static const bool flat = getenv("GPK_LEAF_FLAT") != nullptr;  // the round-1 register-tiled kernel (A/B comparisons)
+  if (flat) {
+    potrf_leaf_kernel<T><<<batch, 256, 0, stream>>>(A, lda, a_bs, logdet, info, pivot_base);
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(potrf_leaf_rec_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM);
+      if (e != cudaSuccess) return -1000 - (int)e;
+      attr_set = true;
+    }
+    potrf_leaf_rec_kernel<T><<<batch, RL_THREADS, RL_SMEM, stream>>>(A, lda, a_bs, logdet, info, pivot_base);
+  }
   GPK_COUNT_LAUNCH();
   GPK_CHECK_LAUNCH();
   return 0;

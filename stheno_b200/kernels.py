@@ -409,16 +409,19 @@ class ScaledKernel(Kernel):
         if not self._flattenable():
             return M.Dense(self._pairwise_dev(x, y, same), x.origin)
         inner = self.k
-        if isinstance(self.scale, torch.Tensor) and self.scale.requires_grad and torch.is_grad_enabled():
-            # a scale that carries a graph: the structured shortcuts below would detach it (float(scale)); the generic
-            # descriptor path keeps it as ``flat.coef_raw`` for the differentiable log-pdf
-            return super()._matrix(x, y, same)
-        if same and isinstance(inner, Linear) and float(self.scale) > 0:
-            return M.LowRank(x.t * float(self.scale) ** 0.5, x.origin)
+        # a scale that carries a graph must not be detached by the structured shortcuts: keep it as a tensor
+        st = self.scale if (isinstance(self.scale, torch.Tensor) and self.scale.requires_grad and torch.is_grad_enabled()) else None
+        sv = float(self.scale.detach()) if isinstance(self.scale, torch.Tensor) else float(self.scale)
+        if same and isinstance(inner, Linear) and sv > 0:
+            if st is not None:
+                return M.LowRank(x.t * st.to(device=x.t.device, dtype=x.t.dtype).sqrt(), x.origin)
+            return M.LowRank(x.t * sv ** 0.5, x.origin)
         if same and isinstance(inner, Delta):
-            v = float(self.scale)
-            return M.fill_diag(v, x.n, x.t.dtype, x.t.device, x.origin) if not x.batch_shape else M.Diagonal(
-                torch.full(x.batch_shape + (x.n,), v, dtype=x.t.dtype, device=x.t.device), x.origin, scalar=v)
+            if st is not None:
+                d = st.to(device=x.t.device, dtype=x.t.dtype).expand(x.batch_shape + (x.n,))
+                return M.Diagonal(d, x.origin, scalar=sv, scalar_t=st)
+            return M.fill_diag(sv, x.n, x.t.dtype, x.t.device, x.origin) if not x.batch_shape else M.Diagonal(
+                torch.full(x.batch_shape + (x.n,), sv, dtype=x.t.dtype, device=x.t.device), x.origin, scalar=sv)
         return super()._matrix(x, y, same)
 
     def render(self):
@@ -463,8 +466,7 @@ class SumKernel(_Join):
     def _matrix(self, x, y, same):
         if self._flattenable():
             # keep Delta parts diagonal: k + s2 * Delta  ->  KernelDense + Diagonal (stays symbolic)
-            kb, cb = _strip_scale(self.b)
-            if same and isinstance(kb, Delta) and not (isinstance(cb, torch.Tensor) and cb.requires_grad and torch.is_grad_enabled()):
+            if same and isinstance(_strip_scale(self.b)[0], Delta):
                 return M.add(self.a._matrix(x, y, same), self.b._matrix(x, y, same))
             return super()._matrix(x, y, same)
         yy = None if same else y

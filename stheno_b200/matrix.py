@@ -370,6 +370,12 @@ class Woodbury(AbstractMatrix):
     def T(self):
         return self
 
+    def needs_grad(self, *others):
+        """True when a gradient has to flow through this matrix (or ``others``): ``logdet`` / ``iqf`` then take the
+        differentiable route of ``generic_grad.py`` (the raw-pointer Schur-complement GEMM would cut the graph)."""
+        ts = (self.lr.left, self.diag_m.diag) + tuple(others)
+        return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in ts)
+
     def schur(self):
         """``(I + U^T D^-1 U)`` as a Dense (r x r) with its cached factor; the n r^2 product runs on the tensor-core
         GEMM (rows of ``U^T D^-1/2`` are K-contiguous)."""

@@ -165,6 +165,8 @@ class AbstractPseudoObservations(AbstractObservations):
         the m^2 n flops of the solve and of ``A = I + W K_n^-1 W^T`` both run on the tensor-core GEMM."""
         p_x, x, noise_x = self.fdd.p, self.fdd.x, self.fdd.noise
         p_z, z, noise_z = self.u.p, self.u.x, self.u.noise
+        if self._wants_grad(measure):
+            return self._compute_grad(measure)
         K_z = M.add(pairwise(measure.kernels[p_z], z), noise_z)  # :286
         self._K_z[id(measure)] = K_z
         K_n = noise_x  # :290
@@ -235,6 +237,54 @@ class AbstractPseudoObservations(AbstractObservations):
         elbo = -0.5 * (det_part + iqf_part + trace_part)
         bs = K_z.shape[:-2]
         self._elbo[id(measure)] = elbo.reshape(bs) if bs else elbo[0]
+
+
+    # -- differentiable route (generic_grad.py): used only when something that feeds the ELBO requires grad -----------------
+    def _wants_grad(self, measure):
+        from ..generic_grad import kernel_needs_grad
+        from ..kernels import Input
+
+        if not torch.is_grad_enabled():
+            return False
+        p_x, p_z = self.fdd.p, self.u.p
+        ks = [measure.kernels[p_z], measure.kernels[p_z, p_x], measure.kernels[p_x]]
+        if any(kernel_needs_grad(k) for k in ks):
+            return True
+        ts = [self.y]
+        for v in (self.fdd.x, self.u.x):
+            if isinstance(v, Input):
+                ts.append(v.t)
+        for nz in (self.fdd.noise, self.u.noise):
+            if isinstance(nz, M.Diagonal):
+                ts.append(nz.diag)
+        return any(isinstance(t, torch.Tensor) and t.requires_grad for t in ts)
+
+    def _compute_grad(self, measure):
+        from ..generic_grad import sparse_compute_torch
+        from ..kernels import Input
+
+        p_x, x, K_n = self.fdd.p, self.fdd.x, self.fdd.noise
+        p_z, z, noise_z = self.u.p, self.u.x, self.u.noise
+        if not isinstance(K_n, M.Diagonal):
+            raise RuntimeError(
+                f'Kernel matrix of observation noise must be diagonal, not "{type(K_n).__name__}".'
+            )
+        if not isinstance(x, Input) or not isinstance(z, Input):
+            raise NotImplementedError("gradients of a sparse approximation over multi-output inputs are not implemented")
+        if isinstance(noise_z, M.Zero):
+            nz = None
+        elif isinstance(noise_z, M.Diagonal):
+            nz = noise_z.diag
+        else:
+            raise NotImplementedError("gradients with a dense inducing-point noise are not implemented")
+        y_bar = uprank(self.y) - measure.means[p_x].dev(x)
+        K_z, LAL, mu, elbo = sparse_compute_torch(
+            self.method, measure.kernels[p_z], measure.kernels[p_z, p_x], measure.kernels[p_x], z.t, x.t, K_n.diag, nz,
+            y_bar, measure.means[p_z].dev(z), B.epsilon)
+        self._K_z[id(measure)] = M.Dense(K_z, z.origin)
+        self._mu[id(measure)] = mu
+        self._A[id(measure)] = M.Dense(LAL, z.origin)
+        self._elbo[id(measure)] = elbo
 
 
 class PseudoObservations(AbstractPseudoObservations):

@@ -236,7 +236,12 @@ class Normal(RandomVector):
                 return self._logpdf_missing(xd, nan, var, out_origin)
         n = var.shape[-1]
         diff = xd if self.mean_is_zero else xd - self._mean_dev()
-        if isinstance(var, (M.Diagonal, M.Woodbury)):
+        if isinstance(var, M.Woodbury) and var.needs_grad(diff):
+            from .generic_grad import woodbury_terms_torch
+
+            ld, q = woodbury_terms_torch(var.lr.left, var.diag_m.diag, diff, B.epsilon)
+            lp = -(ld.unsqueeze(-1) + n * B.log_2_pi + q) / 2
+        elif isinstance(var, (M.Diagonal, M.Woodbury)):
             ld = M.logdet(var)
             q = M.iqf_diag(var, diff)
             lp = -(ld.unsqueeze(-1) + n * B.log_2_pi + q) / 2

@@ -119,3 +119,65 @@ def test_strict_mode_raises_on_non_positive_definite(S):
     finally:
         S.B.strict = False
     assert np.isnan(S.Normal(bad).logpdf(np.array([0.1, 0.2])))
+
+
+@pytest.mark.parametrize("method", ["vfe", "fitc", "dtc"])
+def test_sparse_elbo_gradients_reach_every_parameter(S, method):
+    """``elbo.backward()`` returned a partial gradient (noise only).  Now: gradients w.r.t. kernel variance,
+    length scale, noise and inducing points, against central finite differences of the ORACLE's ELBO."""
+    rng = np.random.default_rng(3)
+    n, m, d = 60, 7, 2
+    x, z, y = rng.standard_normal((n, d)), rng.standard_normal((m, d)), rng.standard_normal(n)
+    cls = {"vfe": S.PseudoObs, "fitc": S.PseudoObsFITC, "dtc": S.PseudoObsDTC}[method]
+    p0 = np.array([1.3, 0.9, 0.2])
+
+    def oracle(p, zz):
+        spec = ("scaled", p[0], ("stretched", p[1], ("matern52",)))
+        return O.sparse_compute(spec, zz, x, p[2], y, method)["elbo"]
+
+    var, ell, noise = (torch.tensor(v, dtype=torch.float64, requires_grad=True) for v in p0)
+    zt = torch.tensor(z, requires_grad=True)
+    f = S.GP(var * S.Matern52().stretch(ell))
+    obs = cls(f(zt), f(torch.tensor(x), noise), torch.tensor(y))
+    elbo = obs.elbo(f.measure)
+    assert abs(float(elbo) - oracle(p0, z)) < 1e-9 * abs(float(elbo))
+    elbo.backward()
+    h = 1e-6
+    for i, t in enumerate((var, ell, noise)):
+        e = np.zeros(3)
+        e[i] = h
+        fd = (oracle(p0 + e, z) - oracle(p0 - e, z)) / (2 * h)
+        assert t.grad is not None and abs(t.grad.item() - fd) < 1e-5 * max(1.0, abs(fd)), (method, i, t.grad, fd)
+    zp, zm = z.copy(), z.copy()
+    zp[2, 1] += h
+    zm[2, 1] -= h
+    fd = (oracle(p0, zp) - oracle(p0, zm)) / (2 * h)
+    assert abs(zt.grad[2, 1].item() - fd) < 1e-5 * max(1.0, abs(fd))
+    # posterior through the differentiable route agrees with the oracle as well
+    mean = (f | obs)(x[:5]).mean
+    mo, _ = O.sparse_posterior(("scaled", p0[0], ("stretched", p0[1], ("matern52",))), z, x, p0[2], y, x[:5], method)
+    np.testing.assert_allclose(S.B.to_numpy(mean), mo, rtol=1e-7, atol=1e-8)
+
+
+def test_woodbury_logpdf_gradients(S):
+    """``GP(s * Linear())(x, noise).logpdf(y)`` keeps the O(n d^2) Woodbury route AND a complete graph."""
+    rng = np.random.default_rng(8)
+    n, d = 50, 3
+    x, y = rng.standard_normal((n, d)), rng.standard_normal(n)
+
+    def oracle(p):
+        return float(O.fdd_logpdf(("scaled", p[0], ("linear",)), x, p[1], y))
+
+    p0 = np.array([0.7, 0.3])
+    s, noise = (torch.tensor(v, dtype=torch.float64, requires_grad=True) for v in p0)
+    fdd = S.GP(s * S.Linear())(torch.tensor(x), noise)
+    assert type(fdd.var).__name__ == "Woodbury"
+    lp = fdd.logpdf(torch.tensor(y))
+    assert abs(float(lp) - oracle(p0)) < 1e-9 * abs(oracle(p0))
+    lp.backward()
+    h = 1e-6
+    for i, t in enumerate((s, noise)):
+        e = np.zeros(2)
+        e[i] = h
+        fd = (oracle(p0 + e) - oracle(p0 - e)) / (2 * h)
+        assert t.grad is not None and abs(t.grad.item() - fd) < 1e-5 * max(1.0, abs(fd)), (i, t.grad, fd)
