@@ -161,6 +161,7 @@ class KernelDense(Dense):
         self.flat, self.xg, self.batch_shape = flat, xg, tuple(batch_shape)
         self.noise_scalar, self.noise_vec, self.noise_t = float(noise_scalar), noise_vec, noise_t
         self.n = xg.shape[2]
+        self.full_precision = False  # set by consumers that read element-wise quantities off the factor (conditioning)
 
     @property
     def dev(self):
@@ -213,12 +214,14 @@ class KernelDense(Dense):
             nt = (self.noise_scalar if nt is None else nt) + scalar_t
         elif nt is not None:
             nt = nt + float(scalar)
-        return KernelDense(self.flat, self.xg, self.batch_shape, self.noise_scalar + float(scalar), nv, self.origin, nt)
+        out = KernelDense(self.flat, self.xg, self.batch_shape, self.noise_scalar + float(scalar), nv, self.origin, nt)
+        out.full_precision = self.full_precision
+        return out
 
     def _factorize(self, rhs_t):
         return ops.chol_from_kernel(self.flat, self.xg.detach(), noise_scalar=self.noise_scalar,
                                     noise_vec=None if self.noise_vec is None else self.noise_vec.detach(),
-                                    jitter=_B.epsilon, rhs_t=rhs_t)
+                                    jitter=_B.epsilon, rhs_t=rhs_t, full_precision=self.full_precision)
 
     def logpdf_grad(self, rhs_t):
         """Differentiable ``logpdf`` ``[B, k]`` w.r.t. kernel scales, length scales / inputs (through ``xg``), noise and

@@ -72,6 +72,8 @@ class Observations(AbstractObservations):
         except KeyError:
             K_x = M.add(pairwise(measure.kernels[self.fdd.p], self.fdd.x), self.fdd.noise)
             K_x = M._densify(K_x, full=True)  # low-rank structure is exploited by logpdf; conditioning uses the dense factor
+            if isinstance(K_x, M.KernelDense):
+                K_x.full_precision = True  # posterior means / variances are read element-wise off this factor
             if isinstance(K_x, M.Dense):
                 diff = self.y - measure.means[self.fdd.p].dev(self.fdd.x)
                 d3, _ = batch_flatten(diff, 2)

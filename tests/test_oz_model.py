@@ -54,6 +54,7 @@ def test_auto_slice_count_heuristic():
     assert ops._well_conditioned(eq_delta, 0.0, None, 1e-12)  # the Delta term is the noise
     assert not ops._well_conditioned(eq, 0.0, None, 1e-12)  # noise-free: only the jitter
     assert not ops._well_conditioned(eq, 1e-9, None, 0.0)
+    assert not ops._well_conditioned(eq, 1e-4, None, 0.0)  # measured: the 7-slice log-pdf error reaches 1e-10 near 1e-4
     assert not ops._well_conditioned(eq, 0.1, object(), 0.0)  # per-point noise: smallest entry unknown on the host
     assert not ops._well_conditioned(lin, 0.1, None, 0.0)  # unbounded kernel
     before = B.precision
