@@ -205,7 +205,7 @@ def _pad_identity(K, n):
     return Kp
 
 
-def chol_from_kernel(flat, xg, *, noise_scalar=0.0, noise_vec=None, jitter=0.0, rhs_t=None):
+def chol_from_kernel(flat, xg, *, noise_scalar=0.0, noise_vec=None, jitter=0.0, rhs_t=None, full_precision=False):
     K = kernel_matrix(flat, xg, noise_scalar=noise_scalar, noise_vec=noise_vec, jitter=jitter)
     n = K.shape[1]
     return _finish(_pad_identity(K, n), n, rhs_t)
