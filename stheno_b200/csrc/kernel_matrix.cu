@@ -12,6 +12,8 @@
 // Reference arithmetic replaced: mlkernels.pairwise for EQ/Matern/Linear/Delta and Scaled/Sum/Product/Stretched
 // (call sites stheno/model/fdd.py:79, stheno/model/observations.py:139,285,286), Dense + Diagonal (fdd.py:79)
 // and B.reg's "+ epsilon I" (README.md:820-830).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gpk {
@@ -257,6 +259,178 @@ __global__ void __launch_bounds__(KM_THREADS) kernel_matrix_kernel(const KmParam
   }
 }
 
+// ---- fast path: ONE stationary factor (coef * EQ / Matern12 / 32 / 52 of one length-scale group) ------------------------
+// The benchmarked configurations all reduce to this (the Delta / noise part is a diagonal term of the epilogue).  Against the
+// generic kernel above (ncu r02: FP64 pipe 20 % busy, 165 registers -> one CTA of 8 warps per SM, issue slots mostly idle):
+//   * the factor kind is a template parameter: no per-element switch, d2 is the only 16-element array kept in registers
+//     (<= 128 registers, >= 2 CTAs per SM so one CTA's TMA wait / transpose / barrier hides under the other's arithmetic);
+//   * fp64 exp = 2^(k/64) table (shared memory) x degree-5 polynomial on |r| <= ln2/128 with a two-part Cody-Waite reduction:
+//     11 FP64-pipe operations instead of the ~25 of the library exp (which also handles overflow / NaN paths that a
+//     non-positive argument never takes); relative error < 3e-16 (table entry rounding + 5 Horner steps), i.e. well
+//     inside the 1e-12 parity budget on K (tests/test_gpu_primitives.py compares at rtol 1e-12 against the oracle).
+__device__ __forceinline__ double fast_exp_nonpos(double x, const double* __restrict__ tab) {
+  // x <= 0.  k = round(x * 64 / ln2); x = k * ln2/64 + r; exp(x) = 2^(k >> 6) * tab[k & 63] * exp(r)
+  const double t = fma(x, 92.332482616893656877, 6755399441055744.0);  // 64 / ln2, 1.5 * 2^52: round-to-nearest in the low bits
+  const int k = __double2loint(t);
+  const double kd = t - 6755399441055744.0;
+  double r = fma(kd, -0.010830424696249145, x);    // ln2/64, high part (fma: one rounding, of a result of size <= ln2/128)
+  r = fma(kd, -3.623510646634843e-19, r);  // ln2/64 minus the high part
+  double p = fma(r, 8.3333333333333332e-3, 4.1666666666666664e-2);
+  p = fma(p, r, 1.6666666666666666e-1);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double v = p * tab[k & 63];
+  const int e = k >> 6;  // <= 0
+  if (e < -1022) return 0.0;  // below the normal range: exp(x) < 2.3e-308 (the library would return a denormal)
+  return __hiloint2double(__double2hiint(v) + e * 1048576, __double2loint(v));
+}
+
+template <typename T, int KIND>
+__device__ __forceinline__ T fast_factor(T d2, int d, const double* tab);
+template <>
+__device__ __forceinline__ double fast_factor<double, GPK_EQ>(double d2, int, const double* tab) {
+  return fast_exp_nonpos(-0.5 * d2, tab);
+}
+template <>
+__device__ __forceinline__ double fast_factor<double, GPK_MATERN12>(double d2, int d, const double* tab) {
+  const double r = (d == 1) ? sqrt(d2) : sqrt(d2 > 1e-30 ? d2 : 1e-30);
+  return fast_exp_nonpos(-r, tab);
+}
+template <>
+__device__ __forceinline__ double fast_factor<double, GPK_MATERN32>(double d2, int d, const double* tab) {
+  const double r = (d == 1) ? sqrt(d2) : sqrt(d2 > 1e-30 ? d2 : 1e-30);
+  const double s = 1.7320508075688772 * r;
+  return (1.0 + s) * fast_exp_nonpos(-s, tab);
+}
+template <>
+__device__ __forceinline__ double fast_factor<double, GPK_MATERN52>(double d2, int d, const double* tab) {
+  const double r = (d == 1) ? sqrt(d2) : sqrt(d2 > 1e-30 ? d2 : 1e-30);
+  const double s = 2.23606797749979 * r;
+  return (1.0 + s + 1.6666666666666667 * d2) * fast_exp_nonpos(-s, tab);
+}
+template <>
+__device__ __forceinline__ float fast_factor<float, GPK_EQ>(float d2, int, const double*) {
+  return expf(-0.5f * d2);
+}
+template <>
+__device__ __forceinline__ float fast_factor<float, GPK_MATERN12>(float d2, int d, const double*) {
+  const float r = (d == 1) ? sqrtf(d2) : sqrtf(d2 > 1e-30f ? d2 : 1e-30f);
+  return expf(-r);
+}
+template <>
+__device__ __forceinline__ float fast_factor<float, GPK_MATERN32>(float d2, int d, const double*) {
+  const float r = (d == 1) ? sqrtf(d2) : sqrtf(d2 > 1e-30f ? d2 : 1e-30f);
+  const float s = 1.7320508075688772f * r;
+  return (1.0f + s) * expf(-s);
+}
+template <>
+__device__ __forceinline__ float fast_factor<float, GPK_MATERN52>(float d2, int d, const double*) {
+  const float r = (d == 1) ? sqrtf(d2) : sqrtf(d2 > 1e-30f ? d2 : 1e-30f);
+  const float s = 2.23606797749979f * r;
+  return (1.0f + s + 1.6666666666666667f * d2) * expf(-s);
+}
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(KM_THREADS, 2) kernel_matrix_fast_kernel(const KmParams p) {
+  const int tile_c = blockIdx.x, tile_r = blockIdx.y, b = blockIdx.z;
+  const bool lower = p.flags & GPK_KM_LOWER;
+  if (lower && (tile_c >> 1) > (tile_r >> 1)) return;
+  const bool same_obj = p.flags & GPK_KM_SAME;
+  const int d = p.d;
+  const int g = p.desc.fac_group[0];
+  const int64_t r0 = (int64_t)tile_r * KM_TILE, c0 = (int64_t)tile_c * KM_TILE;
+
+  extern __shared__ __align__(16) unsigned char km_smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ double tab[64];
+  T* xs = reinterpret_cast<T*>(km_smem);  // [64][d]
+  T* ys = xs + (size_t)KM_TILE * d;       // [64][d]
+  T* yt = ys + (size_t)KM_TILE * d;       // [d][65]
+  const T* xg = static_cast<const T*>(p.xg) + (int64_t)b * p.x_bstride + g * p.xg_gstride + r0 * d;
+  const T* yg = static_cast<const T*>(p.yg) + (int64_t)b * p.y_bstride + g * p.yg_gstride + c0 * d;
+  if (sizeof(T) == 8 && threadIdx.x < 64) tab[threadIdx.x] = exp2((double)threadIdx.x * 0.015625);
+
+  const int xr = (int)max((int64_t)0, min((int64_t)KM_TILE, p.n - r0));
+  const int yr = (int)max((int64_t)0, min((int64_t)KM_TILE, p.n2 - c0));
+  const uint32_t xbytes = (uint32_t)xr * d * sizeof(T), ybytes = (uint32_t)yr * d * sizeof(T);
+  const bool bulk = (xbytes % 16 == 0) && (ybytes % 16 == 0) && ((KM_TILE * d * sizeof(T)) % 16 == 0) &&
+                    (reinterpret_cast<uintptr_t>(xg) % 16 == 0) && (reinterpret_cast<uintptr_t>(yg) % 16 == 0);
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_arrive_expect_tx(&bar, xbytes + ybytes);
+      if (xbytes) bulk_copy_g2s(xs, xg, xbytes, &bar);
+      if (ybytes) bulk_copy_g2s(ys, yg, ybytes, &bar);
+    }
+    mbar_wait(&bar, 0);
+  } else {
+    for (int i = threadIdx.x; i < xr * d; i += KM_THREADS) xs[i] = xg[i];
+    for (int i = threadIdx.x; i < yr * d; i += KM_THREADS) ys[i] = yg[i];
+    __syncthreads();
+  }
+  for (int idx = threadIdx.x; idx < yr * d; idx += KM_THREADS) {
+    const int c = idx / d, k = idx - c * d;
+    yt[(size_t)k * (KM_TILE + 1) + c] = ys[idx];
+  }
+  __syncthreads();
+
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  T d2[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d2[i][j] = T(0);
+  const T* xr_ = xs + (size_t)(ty * 4) * d;
+  const T* yc_ = yt + tx;
+#pragma unroll 2
+  for (int k = 0; k < d; ++k) {
+    T xv[4], yv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xv[i] = xr_[i * d + k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) yv[j] = yc_[(size_t)k * (KM_TILE + 1) + 16 * j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const T df = xv[i] - yv[j];
+        d2[i][j] = fma(df, df, d2[i][j]);
+      }
+  }
+
+  T* out = static_cast<T*>(p.out) + (int64_t)b * p.o_bstride;
+  const T* nv = p.noise_vec ? static_cast<const T*>(p.noise_vec) + (int64_t)b * p.nv_bstride : nullptr;
+  const bool pad_id = p.flags & GPK_KM_PAD_IDENTITY;
+  const T coef = (T)p.desc.coef[0];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + ty * 4 + i;
+    if (r >= p.rows_out) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t c = c0 + tx + 16 * j;
+      if (c >= p.cols_out) continue;
+      T val;
+      if (r >= p.n || c >= p.n2) {
+        val = (pad_id && r == c) ? T(1) : T(0);
+      } else {
+        val = coef * fast_factor<T, KIND>(d2[i][j], d, tab);
+        if (same_obj && r == c) {
+          val += (T)p.noise_scalar;
+          if (nv) val += nv[r];
+          val += (T)p.jitter;
+        }
+      }
+      out[r * p.ldo + c] = val;
+    }
+  }
+}
+
 template <typename T>
 static int launch_kernel_matrix(const gpk_kernel_desc* desc, const T* xg, int64_t xg_gstride, int64_t x_bstride,
                                 int64_t n, const T* yg, int64_t yg_gstride, int64_t y_bstride, int64_t n2, int32_t d,
@@ -290,6 +464,33 @@ static int launch_kernel_matrix(const gpk_kernel_desc* desc, const T* xg, int64_
   p.cols_out = pad ? gpk_round_up(n2) : n2;
   if (p.rows_out == 0 || p.cols_out == 0) return 0;
   if (ldo < p.cols_out) return GPK_ERR_ARG;
+  dim3 grid((unsigned)((p.cols_out + KM_TILE - 1) / KM_TILE), (unsigned)((p.rows_out + KM_TILE - 1) / KM_TILE),
+            (unsigned)batch);
+  if (grid.y > 65535 || grid.z > 65535) return GPK_ERR_UNSUPPORTED;
+  // one stationary factor: the specialised kernel (GPK_K1_GENERIC=1 forces the generic one, for A/B comparisons)
+  static const bool force_generic = getenv("GPK_K1_GENERIC") != nullptr;
+  const int kind0 = desc->fac_kind[0];
+  if (!force_generic && desc->n_terms == 1 && desc->term_begin[1] - desc->term_begin[0] == 1 && kind0 >= GPK_EQ &&
+      kind0 <= GPK_MATERN52 && desc->fac_group[0] >= 0 && desc->fac_group[0] < desc->n_groups) {
+    const size_t fsmem = ((size_t)2 * KM_TILE * d + (size_t)d * (KM_TILE + 1)) * sizeof(T);
+    if (fsmem <= 96 * 1024) {
+      void (*fk)(const KmParams) = nullptr;
+      switch (kind0) {
+        case GPK_EQ: fk = kernel_matrix_fast_kernel<T, GPK_EQ>; break;
+        case GPK_MATERN12: fk = kernel_matrix_fast_kernel<T, GPK_MATERN12>; break;
+        case GPK_MATERN32: fk = kernel_matrix_fast_kernel<T, GPK_MATERN32>; break;
+        default: fk = kernel_matrix_fast_kernel<T, GPK_MATERN52>; break;
+      }
+      if (fsmem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+        if (e != cudaSuccess) return -1000 - (int)e;
+      }
+      fk<<<grid, KM_THREADS, fsmem, (cudaStream_t)stream>>>(p);
+      GPK_COUNT_LAUNCH();
+      GPK_CHECK_LAUNCH();
+      return 0;
+    }
+  }
   const size_t smem = ((size_t)2 * desc->n_groups * KM_TILE * d + (size_t)desc->n_groups * d * (KM_TILE + 1)) * sizeof(T);
   if (smem > 200 * 1024) return GPK_ERR_UNSUPPORTED;
   auto kern = kernel_matrix_kernel<T>;
@@ -297,9 +498,6 @@ static int launch_kernel_matrix(const gpk_kernel_desc* desc, const T* xg, int64_
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -1000 - (int)e;
   }
-  dim3 grid((unsigned)((p.cols_out + KM_TILE - 1) / KM_TILE), (unsigned)((p.rows_out + KM_TILE - 1) / KM_TILE),
-            (unsigned)batch);
-  if (grid.y > 65535 || grid.z > 65535) return GPK_ERR_UNSUPPORTED;
   kern<<<grid, KM_THREADS, smem, (cudaStream_t)stream>>>(p);
   GPK_COUNT_LAUNCH();
   GPK_CHECK_LAUNCH();
