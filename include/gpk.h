@@ -213,6 +213,28 @@ int gpk_transpose_f64(const double* src, int64_t lds, int64_t s_bstride, int64_t
 int gpk_transpose_f32(const float* src, int64_t lds, int64_t s_bstride, int64_t rows, int64_t cols, float* dst,
                       int64_t ldd, int64_t d_bstride, int32_t batch, void* stream);
 
+/* Streamed sparse (inducing-point) accumulation -- AbstractPseudoObservations._compute, stheno/model/observations.py:279-336,
+ * one chunk of `c` data points per call; K_zx (8.6 GB at n = 262144, m = 4096) is never held.  Per chunk, stream-ordered:
+ *   W_c^T = k(x_c, z) L_z^-T  (:285, :301; rows = data points, [c_pad x m_pad], c_pad = round_up(c))
+ *   corr_i = kdiag_i - |w_i|^2 (:304-306);  method 0 (VFE): scalars[2] += sum corr_i / kn_i (:308-310);
+ *   method 1 (FITC): kn_i += corr_i (:311-313);  method 2 (DTC): neither (kdiag may be NULL)
+ *   A    += W diag(1/kn) W^T   (:322; lower 128-tiles of the m_pad x m_pad accumulator, the caller starts it at I)
+ *   prod += W diag(1/kn) ybar  (:327);  scalars[0] += sum log(2 pi kn_i) (:334);  scalars[1] += sum ybar_i^2 / kn_i (:335)
+ * xg / zg: pre-stretched inputs [n_groups][c or m][d] (group strides given); Lz: padded lower factor of K_z + eps I
+ * (gpk_potrf); ws: 16-byte aligned workspace of gpk_sparse_ws_elems(c, m_pad) elements.  The m^2 c flops of the solve and of
+ * the accumulation run on the tensor cores (the int8 emulation when gpk_set_f64_emulation is on and its scratch fits
+ * gpk_f64_emulation_scratch_bytes(m_pad, m_pad, c_pad) and the solve's largest product). */
+int64_t gpk_sparse_ws_elems(int64_t c, int64_t m_pad);
+int gpk_sparse_accumulate_f64(const gpk_kernel_desc* desc_host, const double* xg, int64_t xg_gstride, int64_t c,
+                              const double* zg, int64_t zg_gstride, int64_t m, int32_t d, const double* Lz, int64_t ldl,
+                              int64_t m_pad, const double* kdiag, const double* kn, const double* ybar, int32_t method,
+                              double* A, int64_t lda, double* prod, double* scalars, double* ws, int64_t ws_elems,
+                              void* stream);
+int gpk_sparse_accumulate_f32(const gpk_kernel_desc* desc_host, const float* xg, int64_t xg_gstride, int64_t c,
+                              const float* zg, int64_t zg_gstride, int64_t m, int32_t d, const float* Lz, int64_t ldl,
+                              int64_t m_pad, const float* kdiag, const float* kn, const float* ybar, int32_t method, float* A,
+                              int64_t lda, float* prod, float* scalars, float* ws, int64_t ws_elems, void* stream);
+
 /* Measurement helper (bench.py): runs a register-resident fp64 tensor-core (DMMA) loop on every SM and returns the
  * achieved TFLOP/s -- the denominator of the fp64 roofline -- or a negative error code.  Synchronises the device. */
 double gpk_probe_dmma_tflops(void);

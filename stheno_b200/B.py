@@ -29,6 +29,10 @@ precision = "auto"
 #: default leaves ``info`` on the device (``Chol.info`` / ``Chol.check()``): a failed factorisation then shows as NaN results.
 strict = False
 
+#: Data points per call of the streamed sparse accumulation (``PseudoObs*``): device memory is two ``sparse_chunk x m_pad``
+#: buffers + O(m^2) whatever n is; the reduction length of the tensor-core accumulation is ``sparse_chunk``.
+sparse_chunk = 16384
+
 pi = np.pi
 log_2_pi = float(np.log(2 * np.pi))
 

@@ -49,10 +49,13 @@ _SIGNATURES = {
     "gpk_pad_copy": [_ptr, _i64, _i64, _i64, _i64, _ptr, _i64, _i64, _i64, _i64, _f64, _i32, _i32, _ptr],
     "gpk_symmetrize": [_ptr, _i64, _i64, _i64, _i32, _ptr],
     "gpk_transpose": [_ptr, _i64, _i64, _i64, _i64, _ptr, _i64, _i64, _i32, _ptr],
+    "gpk_sparse_accumulate": [POINTER(KernelDesc), _ptr, _i64, _i64, _ptr, _i64, _i64, _i32, _ptr, _i64, _i64, _ptr, _ptr, _ptr,
+                              _i32, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _ptr],
 }
 _PLAIN = {
     "gpk_version": ([], c_int32),
     "gpk_round_up": ([_i64], _i64),
+    "gpk_sparse_ws_elems": ([_i64, _i64], _i64),
     "gpk_probe_dmma_tflops": ([], c_double),
     "gpk_launch_count": ([], _i64),
     "gpk_launch_count_reset": ([], None),

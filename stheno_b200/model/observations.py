@@ -179,47 +179,20 @@ class AbstractPseudoObservations(AbstractObservations):
         K_z = M._densify(K_z)
         ch_z = K_z.chol()  # :300
         m, m_pad = ch_z.n, ch_z.n_pad
-        # :285 + :301  W^T = (L_z^-1 K_zx)^T, rows = data points, zero padded [B, n_pad, m_pad]
-        Wt, n = _cross_rows(measure.kernels[p_z, p_x], z, x, ch_z)
-        ch_z.solve_rows_(Wt)
+        mean_z = measure.means[p_z].dev(z)
+        y_bar = uprank(self.y) - measure.means[p_x].dev(x)
+        yb3, _ = batch_flatten(y_bar, 2)  # [B, n, 1]
         kn = K_n.diag
         kn3 = kn.reshape(-1, kn.shape[-1])
         if kn3.shape[0] != ch_z.batch:
             kn3 = kn3.expand(ch_z.batch, -1)
-        if self.method in ("vfe", "fitc"):
-            K_x_diag = _elwise_any(measure.kernels[p_x], x, None, True)[..., 0]  # :304
-            _, Q_x_diag = ops.row_dot_sq(Wt, n, m_pad, None)  # :305
-            corr = K_x_diag.reshape(ch_z.batch, n) - Q_x_diag  # :306
-        if self.method == "vfe":
-            trace_part = (corr / kn3).sum(-1)  # :308-310
-        elif self.method == "fitc":
-            kn3 = kn3 + corr  # :311-313
-            trace_part = 0.0
-        elif self.method == "dtc":
-            trace_part = 0.0
-        else:  # pragma: no cover
-            raise ValueError(f'Invalid approximation method "{self.method}".')
-        # A = I + W K_n^-1 W^T  (:322): scale the rows by K_n^-1/2 (in place: W itself is no longer needed),
-        # transpose to the K-contiguous form the tensor-core GEMM wants, SYRK on the lower tiles.
-        n_pad = Wt.shape[1]
-        rs = torch.rsqrt(kn3)
-        Wt[:, :n] *= rs.unsqueeze(-1)
-        WsT = torch.empty(ch_z.batch, m_pad, n_pad, dtype=Wt.dtype, device=Wt.device)
-        ops.transpose(Wt, n_pad, m_pad, out=WsT)  # [B, m_pad, n_pad]
-        del Wt
-        A = torch.zeros(ch_z.batch, m_pad, m_pad, dtype=WsT.dtype, device=WsT.device)
-        A.diagonal(dim1=1, dim2=2).fill_(1.0)
-        ops.gemm_nt(WsT, WsT, A, alpha=1.0, beta=1.0, lower=True)
+        streamed = self._stream_plan(measure, ch_z)
+        if streamed is not None:
+            A, prod, det_kn, yky, trace_part = self._accumulate_streamed(measure, ch_z, kn3, yb3, *streamed)
+        else:
+            A, prod, det_kn, yky, trace_part = self._accumulate_materialised(measure, ch_z, kn3, yb3)
         ops.symmetrize_(A, m_pad)
         A_mat = M.Dense(A[:, :m, :m])
-        # optimal mean (:326-329)
-        mean_z = measure.means[p_z].dev(z)
-        y_bar = uprank(self.y) - measure.means[p_x].dev(x)
-        yb3, _ = batch_flatten(y_bar, 2)  # [B, n, 1]
-        ybs = torch.zeros(ch_z.batch, n_pad, dtype=WsT.dtype, device=WsT.device)
-        ybs[:, :n] = yb3[..., 0] * rs
-        prod, _ = ops.row_dot_sq(WsT, m, n_pad, ybs, want_sq=False)  # [B, m] = W K_n^-1 y_bar  (:327)
-        del WsT
         ch_A = A_mat.chol()
         half = ch_A.half_solve(prod.unsqueeze(1))  # [B, 1, m]  L_A^-1 prod
         sol = ch_A.full_solve(prod.unsqueeze(1))  # A^-1 prod
@@ -234,8 +207,8 @@ class AbstractPseudoObservations(AbstractObservations):
         LAL = ops.gemm_nt(U, Lz_pad)
         self._A[id(measure)] = M.Dense(LAL[:, :m, :m].reshape(K_z.shape), K_z.origin)
         # ELBO (:333-336)
-        det_part = torch.log(2 * B.pi * kn3).sum(-1) + ch_A.logdet
-        iqf_part = (yb3[..., 0] ** 2 / kn3).sum(-1) - (half * half).sum((-1, -2))
+        det_part = det_kn + ch_A.logdet
+        iqf_part = yky - (half * half).sum((-1, -2))
         elbo = -0.5 * (det_part + iqf_part + trace_part)
         bs = K_z.shape[:-2]
         self._elbo[id(measure)] = elbo.reshape(bs) if bs else elbo[0]
@@ -288,6 +261,72 @@ class AbstractPseudoObservations(AbstractObservations):
         self._A[id(measure)] = M.Dense(LAL, z.origin)
         self._elbo[id(measure)] = elbo
 
+
+    # -- the two ways to form A = I + W K_n^-1 W^T, prod = W K_n^-1 ybar and the scalars ------------------------------------
+    def _stream_plan(self, measure, ch_z):
+        """``(flat, scales, x_input, z_input)`` when the problem can be streamed (one problem, numeric inputs, a symmetric
+        cross-kernel that fits one K1 descriptor), else None."""
+        from ..kernels import Input, _is_multi
+
+        p_x, x, p_z, z = self.fdd.p, self.fdd.x, self.u.p, self.u.x
+        if ch_z.batch != 1 or _is_multi(x) or _is_multi(z) or not isinstance(x, Input) or not isinstance(z, Input):
+            return None
+        if x.batch_shape or z.batch_shape:
+            return None
+        k_zx = measure.kernels[p_z, p_x]
+        if not k_zx.symmetric:
+            return None
+        flat, scales = k_zx._flat()
+        if flat is None or not flat.terms:
+            return None
+        return flat, scales, x, z
+
+    def _accumulate_streamed(self, measure, ch_z, kn3, yb3, flat, scales, x, z):
+        """``gpk_sparse_accumulate`` over chunks of data points: O(chunk m + m^2) device memory."""
+        acc = ops.SparseAccumulator(flat, z.scaled(scales), ch_z, self.method, chunk=B.sparse_chunk)
+        xg = x.scaled(scales)  # [G, 1, n, d]
+        n = x.n
+        kd = None
+        if self.method in ("vfe", "fitc"):
+            kd = _elwise_any(measure.kernels[self.fdd.p], x, None, True)[..., 0].reshape(-1)  # :304
+        kn1, yb1 = kn3[0], yb3[0, :, 0]
+        for a in range(0, n, acc.chunk):
+            b_ = min(n, a + acc.chunk)
+            acc.add(xg[:, :, a:b_], None if kd is None else kd[a:b_], kn1[a:b_], yb1[a:b_])
+        sc = acc.scalars
+        return acc.A, acc.prod[: ch_z.n].unsqueeze(0), sc[0].reshape(1), sc[1].reshape(1), sc[2].reshape(1)
+
+    def _accumulate_materialised(self, measure, ch_z, kn3, yb3):
+        """Batched / multi-output / non-flattenable problems: ``W^T = K_xz L_z^-T`` held as one ``[B, n_pad, m_pad]`` buffer."""
+        p_x, x = self.fdd.p, self.fdd.x
+        p_z, z = self.u.p, self.u.x
+        m, m_pad = ch_z.n, ch_z.n_pad
+        Wt, n = _cross_rows(measure.kernels[p_z, p_x], z, x, ch_z)  # :285
+        ch_z.solve_rows_(Wt)  # :301
+        trace_part = torch.zeros(ch_z.batch, dtype=Wt.dtype, device=Wt.device)
+        if self.method in ("vfe", "fitc"):
+            K_x_diag = _elwise_any(measure.kernels[p_x], x, None, True)[..., 0]  # :304
+            _, Q_x_diag = ops.row_dot_sq(Wt, n, m_pad, None)  # :305
+            corr = K_x_diag.reshape(ch_z.batch, n) - Q_x_diag  # :306
+            if self.method == "vfe":
+                trace_part = (corr / kn3).sum(-1)  # :308-310
+            else:
+                kn3 = kn3 + corr  # :311-313
+        n_pad = Wt.shape[1]
+        rs = torch.rsqrt(kn3)
+        Wt[:, :n] *= rs.unsqueeze(-1)
+        WsT = torch.empty(ch_z.batch, m_pad, n_pad, dtype=Wt.dtype, device=Wt.device)
+        ops.transpose(Wt, n_pad, m_pad, out=WsT)
+        del Wt
+        A = torch.zeros(ch_z.batch, m_pad, m_pad, dtype=WsT.dtype, device=WsT.device)
+        A.diagonal(dim1=1, dim2=2).fill_(1.0)
+        ops.gemm_nt(WsT, WsT, A, alpha=1.0, beta=1.0, lower=True)  # :322
+        ybs = torch.zeros(ch_z.batch, n_pad, dtype=WsT.dtype, device=WsT.device)
+        ybs[:, :n] = yb3[..., 0] * rs
+        prod, _ = ops.row_dot_sq(WsT, m, n_pad, ybs, want_sq=False)  # :327
+        det_kn = torch.log(2 * B.pi * kn3).sum(-1)
+        yky = (yb3[..., 0] ** 2 / kn3).sum(-1)
+        return A, prod, det_kn, yky, trace_part
 
 class PseudoObservations(AbstractPseudoObservations):
     """VFE (Titsias, 2009)."""

@@ -497,6 +497,67 @@ def kernel_rows_padded(flat, xsg, xg, chol):
     return out
 
 
+SPARSE_METHOD = {"vfe": 0, "fitc": 1, "dtc": 2}
+
+
+class SparseAccumulator:
+    """Streamed ``AbstractPseudoObservations._compute`` (``stheno/model/observations.py:279-336``) for ONE problem (no batch
+    dimension): the data are walked in chunks of ``chunk`` points through ``gpk_sparse_accumulate``; ``K_zx`` is never held.
+
+    ``A [1, m_pad, m_pad]`` starts at the identity and receives ``W K_n^-1 W^T`` on its lower tiles, ``prod [m_pad]`` receives
+    ``W K_n^-1 ybar``, ``scalars`` = (sum log(2 pi K_n), sum ybar^2 / K_n, trace part).  Device memory: two
+    ``chunk x m_pad`` buffers + ``A``."""
+
+    def __init__(self, flat, zg, ch_z, method, chunk=16384):
+        _require_cuda(zg, ch_z.W)
+        if ch_z.batch != 1 or zg.shape[1] != 1:
+            raise ValueError("SparseAccumulator handles a single problem (batched sparse problems use the materialised path)")
+        self.flat, self.zg, self.ch, self.method = flat, zg.contiguous(), ch_z, SPARSE_METHOD[method]
+        self.m, self.m_pad, self.d = ch_z.n, ch_z.n_pad, zg.shape[3]
+        self.chunk = int(chunk)
+        dt, dev = ch_z.dtype, ch_z.device
+        self.A = torch.zeros(1, self.m_pad, self.m_pad, dtype=dt, device=dev)
+        self.A.diagonal(dim1=1, dim2=2).fill_(1.0)
+        self.prod = torch.zeros(self.m_pad, dtype=dt, device=dev)
+        self.scalars = torch.zeros(3, dtype=dt, device=dev)
+        self.lib = _lib.load()
+        self.ws = None
+
+    def _workspace(self, c):
+        need = int(self.lib.gpk_sparse_ws_elems(c, self.m_pad))
+        if self.ws is None or self.ws.numel() < need:
+            self.ws = torch.empty(need, dtype=self.ch.dtype, device=self.ch.device)
+        if self.ch.dtype == torch.float64:
+            # the emulation scratch has to hold the largest product of the solve and the K = c accumulation
+            slices = _oz_slices(False)
+            c_pad, h = round_up(c), round_up(self.m_pad // 2)
+            need_b = 0
+            if slices:
+                f = self.lib.gpk_f64_emulation_scratch_bytes
+                need_b = max(f(self.m_pad, self.m_pad, c_pad, slices), f(c_pad, self.m_pad - h + TILE, h, slices))
+            _set_emulation(self.ch.device, slices, need_b)
+        return self.ws
+
+    def add(self, xg_chunk, kdiag, kn, ybar):
+        """One chunk: ``xg_chunk [G, 1, c, d]`` pre-stretched points, ``kdiag / kn / ybar [c]`` (``kdiag`` None for DTC)."""
+        _require_cuda(xg_chunk, kdiag, kn, ybar)
+        xg_chunk = xg_chunk.contiguous()
+        c = xg_chunk.shape[2]
+        if c == 0:
+            return
+        ws = self._workspace(c)
+        kd = None if kdiag is None else kdiag.contiguous()
+        kn, ybar = kn.contiguous(), ybar.contiguous()
+        Lp = self.ch.L_padded()
+        desc = self.flat.desc()
+        rc = _fn("gpk_sparse_accumulate", self.ch.dtype)(
+            ctypes.byref(desc), _ptr(xg_chunk), xg_chunk.stride(0), c, _ptr(self.zg), self.zg.stride(0), self.m, self.d,
+            _ptr(Lp), Lp.stride(1), self.m_pad, _ptr(kd), _ptr(kn), _ptr(ybar), self.method, _ptr(self.A), self.A.stride(1),
+            _ptr(self.prod), _ptr(self.scalars), _ptr(ws), ws.numel(), _stream(),
+        )
+        check(rc, "gpk_sparse_accumulate")
+
+
 def gemm_profile(enable):
     """Switch the in-situ event timing of the fp64 GEMM kernel on / off (clears the record)."""
     _lib.load().gpk_gemm_profile_enable(1 if enable else 0)

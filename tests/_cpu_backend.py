@@ -226,6 +226,39 @@ def kernel_rows_padded(flat, xsg, xg, chol):
     return out
 
 
+class SparseAccumulator:
+    """torch-CPU stand-in of ``ops.SparseAccumulator`` (same interface and accumulation semantics, chunk by chunk)."""
+
+    def __init__(self, flat, zg, ch_z, method, chunk=16384):
+        self.flat, self.zg, self.ch, self.method, self.chunk = flat, zg, ch_z, method, int(chunk)
+        self.m, self.m_pad = ch_z.n, ch_z.n_pad
+        self.A = torch.eye(self.m_pad, dtype=ch_z.dtype).reshape(1, self.m_pad, self.m_pad).clone()
+        self.prod = torch.zeros(self.m_pad, dtype=ch_z.dtype)
+        self.scalars = torch.zeros(3, dtype=ch_z.dtype)
+
+    def add(self, xg_chunk, kdiag, kn, ybar):
+        c = xg_chunk.shape[2]
+        Wt = torch.zeros(1, c, self.m_pad, dtype=self.ch.dtype)
+        Wt[:, :, : self.m] = _eval(self.flat, xg_chunk, self.zg, False)
+        self.ch.solve_rows_(Wt)
+        W = Wt[0].T  # [m_pad, c]
+        kn = kn.clone()
+        if self.method in ("vfe", "fitc"):
+            corr = kdiag - (W * W).sum(0)
+            if self.method == "vfe":
+                self.scalars[2] += (corr / kn).sum()
+            else:
+                kn = kn + corr
+        Ws = W / kn
+        upd = Ws @ W.T
+        tr = torch.arange(self.m_pad)[:, None] // TILE
+        tc = torch.arange(self.m_pad)[None, :] // TILE
+        self.A[0] += torch.where(tc <= tr, upd, torch.zeros_like(upd))  # lower 128-tiles only, like the SYRK
+        self.prod += Ws @ ybar
+        self.scalars[0] += torch.log(2 * math.pi * kn).sum()
+        self.scalars[1] += (ybar * ybar / kn).sum()
+
+
 def launch_count(reset=False):
     return 0
 
