@@ -1,6 +1,7 @@
 """Multi-output glue: kernels / means over tuples of FDDs (``stheno/mo/kernel.py:14-99``, ``mo/mean.py:9-46``,
 ``mo/input.py:7-36``).  The joint covariance of several processes is the block matrix ``[[k_{p_i p_j}(x_i, x_j)]]``;
-each block is one fused kernel-matrix launch written straight into its place of the joint matrix."""
+each block is one fused kernel-matrix launch written straight into its place of the joint matrix -- or, when the joint is
+factorised, of the padded lower-triangular workspace (``matrix.BlockDense``)."""
 import torch
 
 from .. import matrix as M
@@ -84,6 +85,9 @@ class CrossKernel(Kernel):
 def _block(rows):
     """``B.block``: assemble a dense block matrix from a grid of structured blocks."""
     org = next((b.origin for r in rows for b in r if getattr(b, "origin", None) is not None), None)
+    if M.BlockDense.eligible(rows):
+        # kept as a grid: K1 writes every block straight into its place when numbers are needed (matrix.BlockDense)
+        return M.BlockDense(rows, org)
     dense_rows = [torch.cat([M.dense(b) for b in r], dim=-1) for r in rows]
     return M.Dense(torch.cat(dense_rows, dim=-2), org)
 

@@ -67,6 +67,32 @@ def kernel_matrix(flat, xg, yg=None, *, same=None, noise_scalar=0.0, noise_vec=N
     return K
 
 
+KM_LOWER, KM_SAME, KM_PAD_IDENTITY, KM_PAD_ZERO = 1, 2, 4, 8
+
+
+def _km_launch(flat, xg, yg, n, n2, d, flags, noise_scalar, noise_vec, jitter, out, ldo, o_bstride, batch):
+    """Stand-in of the raw K1 launch: ``out`` is a (possibly strided) view ``[B, >= n, >= n2]`` written in place."""
+    same = bool(flags & KM_SAME)
+    K = kernel_matrix(flat, xg, None if (same and yg is xg) else yg, same=same, noise_scalar=noise_scalar if same else 0.0,
+                      noise_vec=noise_vec if same else None, jitter=jitter if same else 0.0)
+    out[:, :n, :n2] = K
+
+
+def _new_workspace(B, n, k, device, dtype, rhs_t):
+    n_pad = round_up(max(n, 1))
+    extra = round_up(k) if k > 0 else 0
+    W = torch.zeros(B, n_pad + extra, n_pad, dtype=dtype)
+    if extra:
+        W[:, n_pad : n_pad + k, :n] = rhs_t
+    return W, n_pad, extra
+
+
+def _potrf(W, n, n_pad, extra, k, well_conditioned=False):
+    Kp = torch.tril(W[:, :n_pad]) + torch.tril(W[:, :n_pad], -1).transpose(1, 2)
+    rhs = W[:, n_pad : n_pad + k, :n].clone() if k else None
+    return _finish(Kp, n, rhs)
+
+
 def kernel_diag(flat, xg, yg=None, *, same=None):
     if yg is None:
         yg, same = xg, (True if same is None else same)

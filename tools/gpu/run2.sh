@@ -4,8 +4,8 @@ set -u
 mkdir -p gpurun_out
 echo "== leaf A/B"; timeout 600 python tools/time_leaf.py 2>&1 | tee gpurun_out/r02_leaf_ab.jsonl | cut -c1-1800
 echo "== K1 A/B"; timeout 300 python tools/time_k1.py 2>&1 | tee gpurun_out/r02_k1_ab.jsonl | cut -c1-1800
-echo "== pytest gpu (without the C4/C5 full-size oracle tests)"
-timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider -k "not c4_full_size and not c5_full_size" 2>&1 | tail -25 | tee gpurun_out/r02b_pytest_gpu.log
+echo "== pytest gpu (all, incl. the full-size oracle tests)"
+timeout 1800 python -m pytest tests -m gpu -q -s -p no:cacheprovider --durations=8 2>&1 | grep -v "^conditioning sweep" | tail -40 | tee gpurun_out/r02b_pytest_gpu.log
 echo "== bench"
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02b_bench_n1.json 2> gpurun_out/r02b_bench_n1.err; echo "bench rc=$?"; tail -c 600 gpurun_out/r02b_bench_n1.err
 python - <<'P'
