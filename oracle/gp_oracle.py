@@ -182,6 +182,30 @@ def _kernel(spec, x, y, d2fn, dfn, same):
             return np.concatenate([np.sin(a), np.cos(a)], axis=-1)
 
         return _kernel(spec[2], u(x), u(y), d2fn, dfn, same)
+    if kind == "diff":
+        # mlkernels DerivativeKernel [UPSTREAM-RECALLED] behind ``GP.diff`` (``stheno/model/measure.py:343-360``):
+        # d/dx_{d1} d/dy_{d2} k(x, y), ``None`` = no derivative in that argument.  Closed form for k = EQ().stretch(ell)
+        # (the kernel of the reference's own derivative test, ``tests/model/test_model.py:510-529``).
+        (d1, d2), inner = spec[1], spec[2]
+        ell = 1.0
+        if inner[0] == "stretched":
+            ell, inner = float(inner[1]), inner[2]
+        if inner != ("eq",):
+            raise ValueError("oracle derivative kernels: EQ().stretch(ell) only")
+        xs, ys = _uprank(x) / ell, _uprank(y) / ell
+        k = np.exp(-0.5 * d2fn(xs, ys))
+        pair = d2fn is pw_dists2
+
+        def delta(dim):  # x_dim - y_dim, pairwise or element-wise
+            if pair:
+                return xs[..., :, None, dim] - ys[..., None, :, dim]
+            return (xs[..., :, dim] - ys[..., :, dim])[..., None]
+
+        if d1 is not None and d2 is not None:
+            return ((1.0 if d1 == d2 else 0.0) - delta(d1) * delta(d2)) * k / ell**2
+        if d1 is not None:
+            return -delta(d1) * k / ell
+        return delta(d2) * k / ell
     raise ValueError(f"unknown kernel {kind!r}")
 
 

@@ -22,7 +22,7 @@ __all__ = [
     "Kernel", "EQ", "Exp", "Matern12", "Matern32", "Matern52", "Linear", "Delta", "OneKernel", "ZeroKernel",
     "ScaledKernel", "SumKernel", "ProductKernel", "StretchedKernel", "ReversedKernel", "PosteriorKernel",
     "SubspaceKernel", "Mean", "ZeroMean", "OneMean", "ScaledMean", "SumMean", "ProductMean", "StretchedMean",
-    "FunctionMean", "PosteriorMean", "mean_var", "mean_var_diag", "num_elements", "pairwise", "elwise",
+    "FunctionMean", "DerivativeMean", "DerivativeKernel", "PosteriorMean", "mean_var", "mean_var_diag", "num_elements", "pairwise", "elwise",
 ]
 
 
@@ -160,6 +160,14 @@ class Kernel:
         """``k.transform(f)``: ``k(f(x), f(y))``; ``k.transform(f1, f2)`` per input, ``None`` = identity (``measure.py:343``).
         ``f`` receives the points as a device tensor ``[..., n, d]`` and returns a tensor (or anything array-like)."""
         return _map_kernel(self, "transform", fs)
+
+    def diff(self, *dims):
+        """``k.diff(dim)``: ``d^2 k / dx_dim dy_dim``; ``k.diff(d1, d2)`` differentiates the arguments separately, ``None`` =
+        not at all (the cross-kernels of ``stheno/model/measure.py:343-360``; mlkernels ``DerivativeKernel``)."""
+        d1, d2 = (dims[0], dims[0]) if len(dims) == 1 else dims
+        if isinstance(self, ZeroKernel) or (d1 is None and d2 is None):
+            return self
+        return DerivativeKernel(self, d1, d2)
 
     def __add__(self, other):
         other = _as_kernel(other)
@@ -699,6 +707,71 @@ def _map_kernel(k, kind, params):
     return MappedKernel(k, m1, m2)
 
 
+class DerivativeKernel(Kernel):
+    """``d^a/dx_{d1} d^b/dy_{d2} k(x, y)`` (``a, b`` in {0, 1}; mlkernels ``DerivativeKernel`` behind ``GP.diff``,
+    ``stheno/model/measure.py:343-360``).  Evaluated by forward-mode differentiation (``torch.func.jvp``, nested for the mixed
+    second derivative) of the differentiable restatement of the flattened inner kernel (``generic_grad.kernel_torch``):
+    ``K[i, j]`` depends on ``x`` only through row ``i``, so ONE tangent with ``e_{d1}`` in every row gives every
+    ``dK[i, j] / dx_i[d1]`` at once.  SURVEY 8f rank 3 (off the benchmarked path; the result is an ordinary dense matrix that
+    the hand-written factorisation / solves then consume)."""
+
+    def __init__(self, k, d1, d2):
+        self.k, self.d1, self.d2 = k, d1, d2
+
+    @property
+    def symmetric(self):
+        return self.k.symmetric and self.d1 == self.d2
+
+    def reversed(self):
+        return self if self.symmetric else DerivativeKernel(self.k.reversed(), self.d2, self.d1)
+
+    def _deriv(self, fn, xt, yt):
+        from torch.func import jvp
+
+        def tangent(t, d):
+            e = torch.zeros_like(t)
+            e[..., d] = 1.0
+            return e
+
+        if self.d1 is not None and self.d2 is not None:
+            def inner(yv):
+                return jvp(lambda xv: fn(xv, yv), (xt,), (tangent(xt, self.d1),))[1]
+
+            return jvp(inner, (yt,), (tangent(yt, self.d2),))[1]
+        if self.d1 is not None:
+            return jvp(lambda xv: fn(xv, yt), (xt,), (tangent(xt, self.d1),))[1]
+        return jvp(lambda yv: fn(xt, yv), (yt,), (tangent(yt, self.d2),))[1]
+
+    def _pairwise_dev(self, x, y, same):
+        from .generic_grad import kernel_torch
+
+        with torch.enable_grad():
+            out = self._deriv(lambda a, b: kernel_torch(self.k, a, b), x.t.detach(), (x if same else y).t.detach().clone())
+        return out.detach()
+
+    def _elwise_dev(self, x, y, same):
+        from .generic_grad import kernel_torch
+
+        def fn(a, b):  # elementwise: pair i with i
+            return kernel_torch(self.k, a.unsqueeze(-2), b.unsqueeze(-2))[..., 0, 0]
+
+        with torch.enable_grad():
+            out = self._deriv(fn, x.t.detach(), (x if same else y).t.detach().clone())
+        return out.detach().unsqueeze(-1)
+
+    def _matrix(self, x, y, same):
+        return M.Dense(self._pairwise_dev(x, y, same), x.origin)
+
+    def render(self):
+        if self.d1 == self.d2:
+            return f"d({self.d1}) {_paren(self.k)}"
+        return f"d({self.d1}, {self.d2}) {_paren(self.k)}"
+
+    @property
+    def stationary(self):
+        return self.k.stationary
+
+
 class FunctionScaledKernel(Kernel):
     """``g1(x) k(x, y) g2(y)`` for user functions ``g`` (``None`` = 1): ``f * k`` and the one-sided
     ``TensorProductKernel(f, ones) * k`` of ``GP * function`` (``stheno/model/measure.py:241-251``).  The inner kernel is
@@ -1012,6 +1085,10 @@ class Mean:
     def transform(self, f):
         return self if self.is_zero else MappedMean(self, InputMap("transform", f))
 
+    def diff(self, dim=0):
+        """``m.diff(dim)``: ``dm/dx_dim`` (``stheno/model/measure.py:357``)."""
+        return self if self.is_zero else DerivativeMean(self, dim)
+
     def render(self):
         return type(self).__name__ + "()"
 
@@ -1111,6 +1188,31 @@ class MappedMean(Mean):
 
     def render(self):
         return f"{self.m.render()} {self.imap.render()}"
+
+
+class DerivativeMean(Mean):
+    """``dm/dx_dim`` by forward-mode differentiation of the mean's torch evaluation (user functions, constants, sums /
+    products / scalings of those)."""
+
+    def __init__(self, m, dim):
+        self.m, self.dim = m, dim
+
+    def _dev(self, x):
+        from torch.func import jvp
+
+        def fn(t):
+            xi = Input.__new__(Input)
+            xi.origin, xi._groups, xi.src, xi.t = x.origin, {}, None, t
+            return self.m.dev(xi)
+
+        e = torch.zeros_like(x.t)
+        e[..., self.dim] = 1.0
+        with torch.enable_grad():
+            out = jvp(fn, (x.t.detach(),), (e,))[1]
+        return out.detach()
+
+    def render(self):
+        return f"d({self.dim}) {self.m.render()}"
 
 
 class FunctionMean(Mean):

@@ -38,6 +38,28 @@ def _is_numeric(v):
     return isinstance(v, (int, float, np.number, np.ndarray, torch.Tensor))
 
 
+def _central_fdm(order, deriv, factor=1e8):
+    """Grid, coefficients and step of ``fdm.central_fdm(order, deriv, adapt=0, factor=factor)`` [UPSTREAM-RECALLED: fdm is an
+    un-vendored dependency].  Central integer grid of ``order`` points (even orders skip the centre); the coefficients solve the Taylor conditions
+    ``sum_i c_i g_i^k = k! [k == deriv]``, ``k < order``; the step minimises the bound ``c1 / h^deriv + c2 h^(order - deriv)`` with
+    ``c1 = 1e-16 * factor * sum|c|`` (round-off of the function values) and ``c2 = sum|c g^order| / order!`` (truncation)."""
+    import math
+
+    half = order // 2
+    if order % 2 == 0:  # even: integer points without the centre (order 2 -> [-1, 1]: pinned by README.md:292-293)
+        grid = np.concatenate([np.arange(-half, 0), np.arange(1, half + 1)]).astype(np.float64)
+    else:
+        grid = np.arange(-half, half + 1).astype(np.float64)
+    V = np.vander(grid, order, increasing=True).T  # V[k, i] = g_i^k
+    rhs = np.zeros(order)
+    rhs[deriv] = math.factorial(deriv)
+    coefs = np.linalg.solve(V, rhs)
+    c1 = 1e-16 * factor * np.sum(np.abs(coefs))
+    c2 = np.sum(np.abs(coefs * grid**order)) / math.factorial(order)
+    step = (deriv / (order - deriv) * c1 / c2) ** (1.0 / order)
+    return grid, coefs, step
+
+
 class GP(RandomProcess):
     """``GP([mean,] kernel, *, measure=None, name=None)``; ``GP()`` makes an unattached handle."""
 
@@ -151,10 +173,23 @@ class GP(RandomProcess):
             measure.transform(res, self, f)
         return res
 
-    def _out_of_scope(self, *a, **k):
-        raise NotImplementedError("outside the GP-inference hot-path scope (SURVEY.md 8f rank 3)")
+    def diff(self, dim=0):
+        """``f.diff(dim)``: the derivative process (``gp.py:218-223``)."""
+        res = GP()
+        for measure in self._measures:
+            measure.diff(res, self, dim)
+        return res
 
-    diff = diff_approx = _out_of_scope
+    def diff_approx(self, deriv=1, order=6):
+        """Finite-difference approximation of the ``deriv``-th derivative as a linear combination of shifted copies of this
+        GP (``gp.py:225-244``).  The reference takes grid, coefficients and step from ``fdm.central_fdm(order, deriv, adapt=0,
+        factor=1e8)``; restated here (``_central_fdm``) and pinned on the README literal (``README.md:292-293``: order 2 ->
+        step 1.414213562373095e-4, coefficients -0.5 / 0.5)."""
+        grid, coefs, step = _central_fdm(order, deriv)
+        df = 0
+        for g, c in zip(grid, coefs):
+            df = df + float(c) * self.shift(float(-g * step))
+        return df / step**deriv
 
     @property
     def stationary(self):

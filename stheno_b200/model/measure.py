@@ -193,6 +193,15 @@ class Measure:
             lambda j: self.kernels[p, j].transform(f, None),
         )
 
+    def diff(self, p_diff, p, dim=0):
+        """``measure.py:343-360``: the derivative process, its kernel ``d^2 k / dx dy`` and cross-kernels ``dk / dx``."""
+        return self._update(
+            p_diff,
+            self.means[p].diff(dim),
+            self.kernels[p].diff(dim),
+            lambda j: self.kernels[p, j].diff(dim, None),
+        )
+
     def condition(self, *args):
         """``measure | obs`` -> posterior measure whose means / kernels are built on demand (``measure.py:362-401``)."""
         if len(args) == 1 and isinstance(args[0], AbstractObservations):
