@@ -15,3 +15,23 @@ print({k:b[k] for k in ('value','ms_per_step')}, b['e2e']['value'], b['native_fp
 P
 echo "== launch list"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02b_launches_logpdf16384.csv python tools/one_logpdf.py 16384 1 > gpurun_out/r02b_launches.log 2>&1; echo "ncu rc=$?"
+echo "== C3 launch list (64 x 2048 fp32)"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02b_launches_c3_64x2048.csv python tools/one_c3.py 64 1 > gpurun_out/r02b_launches_c3.log 2>&1; echo "ncu rc=$?"
+python tools/launch_summary.py gpurun_out/r02b_launches_c3_64x2048.csv | head -16
+python tools/launch_summary.py gpurun_out/r02b_launches_logpdf16384.csv | head -12
+echo "== NB_OUTER experiment"
+for nb in 768 1024; do GPK_NB_OUTER=$nb timeout 200 python - <<'P'
+import os, torch, sys
+sys.path.insert(0, ".")
+import stheno_b200 as S
+g = torch.Generator(device="cuda").manual_seed(0)
+x = torch.randn(16384, 8, device="cuda", dtype=torch.float64, generator=g); y = torch.randn(16384, device="cuda", dtype=torch.float64, generator=g)
+k = S.EQ().stretch(2.0) + 0.1 * S.Delta()
+for _ in range(3): lp = S.GP(k)(x).logpdf(y)
+torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10): lp = S.GP(k)(x).logpdf(y)
+e1.record(); torch.cuda.synchronize()
+print("NB_OUTER", os.environ["GPK_NB_OUTER"], "logpdf ms", e0.elapsed_time(e1) / 10, float(lp))
+P
+done
