@@ -55,8 +55,10 @@ def build_library(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {s}")
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = LIB + ".tmp"
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB)  # atomic: a snapshot of the tree (gpurun) never sees a half-written library
     return LIB
 
 
