@@ -49,7 +49,8 @@ enum gpk_kind {
   GPK_MATERN52 = 3, /* (1 + sqrt5 r + 5 r^2 / 3) exp(-sqrt5 r)      */
   GPK_LINEAR = 4,   /* <x, y>                                       */
   GPK_DELTA = 5,    /* same inputs: [i == j]; else [r^2 < 1e-10]    */
-  GPK_ONE = 6       /* 1                                            */
+  GPK_ONE = 6,      /* 1                                            */
+  GPK_RQ = 7        /* (1 + r^2 / (2 alpha))^-alpha, alpha = fac_param[f] (mlkernels RQ; README.md:1076-1088) */
 };
 
 #define GPK_MAX_TERMS 8
@@ -63,6 +64,7 @@ typedef struct gpk_kernel_desc {
   int32_t fac_kind[GPK_MAX_FACTORS];
   int32_t fac_group[GPK_MAX_FACTORS];
   double coef[GPK_MAX_TERMS];
+  double fac_param[GPK_MAX_FACTORS]; /* per-factor shape parameter (GPK_RQ: alpha); unused by the other kinds */
 } gpk_kernel_desc;
 
 /* flags for gpk_kernel_matrix_* */

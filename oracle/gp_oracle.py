@@ -106,7 +106,7 @@ def ew_dists(x, y):
 # L2: kernels  (mlkernels.pairwise / elwise)  [UPSTREAM-RECALLED]
 #
 # A kernel is a nested tuple:
-#   ("eq",) ("matern12",) ("matern32",) ("matern52",) ("linear",) ("delta",) ("one",) ("zero",)
+#   ("eq",) ("rq", alpha) ("matern12",) ("matern32",) ("matern52",) ("linear",) ("delta",) ("one",) ("zero",)
 #   ("scaled", c, k)  ("sum", k1, k2)  ("product", k1, k2)  ("stretched", ell, k)
 #   input maps (``GP.shift/select/transform``, ``stheno/model/measure.py:272-345``; the second entry of a pair maps the second
 #   argument, ``None`` = untouched):  ("shifted", c, k)  ("selected", dims, k)  ("transformed", f, k)  and per-argument
@@ -121,6 +121,10 @@ def _kernel(spec, x, y, d2fn, dfn, same):
     kind = spec[0]
     if kind == "eq":
         return np.exp(-0.5 * d2fn(x, y))
+    if kind == "rq":
+        # mlkernels RQ(alpha) [UPSTREAM-RECALLED]: (1 + r^2 / (2 alpha))^-alpha ; used in README.md:1076-1088
+        alpha = float(spec[1])
+        return (1 + d2fn(x, y) / (2 * alpha)) ** (-alpha)
     if kind == "matern12":
         return np.exp(-dfn(x, y))
     if kind == "matern32":

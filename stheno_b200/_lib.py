@@ -16,7 +16,7 @@ GPK_MAX_GROUPS = 8
 
 KM_LOWER, KM_SAME, KM_PAD_IDENTITY, KM_PAD_ZERO = 1, 2, 4, 8
 
-KIND = {"eq": 0, "matern12": 1, "matern32": 2, "matern52": 3, "linear": 4, "delta": 5, "one": 6}
+KIND = {"eq": 0, "matern12": 1, "matern32": 2, "matern52": 3, "linear": 4, "delta": 5, "one": 6, "rq": 7}
 
 
 class KernelDesc(Structure):
@@ -27,6 +27,7 @@ class KernelDesc(Structure):
         ("fac_kind", c_int32 * GPK_MAX_FACTORS),
         ("fac_group", c_int32 * GPK_MAX_FACTORS),
         ("coef", c_double * GPK_MAX_TERMS),
+        ("fac_param", c_double * GPK_MAX_FACTORS),
     ]
 
 

@@ -61,8 +61,12 @@ __device__ __forceinline__ float t_sqrt<float>(float v) {
 
 // phi(kind) from squared distance d2 / dot product.  d == 1 mirrors lab's |x - y| special case (no 1e-30 clamp).
 template <typename T>
-__device__ __forceinline__ T eval_factor(int kind, T d2, T dot, bool same_point, bool same_obj, int d) {
+__device__ __forceinline__ T eval_factor(int kind, T d2, T dot, bool same_point, bool same_obj, int d, double param = 0.0) {
   switch (kind) {
+    case GPK_RQ: {  // (1 + r^2 / (2 alpha))^-alpha
+      const double a = param;
+      return (T)exp(-a * log1p((double)d2 / (2.0 * a)));
+    }
     case GPK_EQ:
       return t_exp<T>(T(-0.5) * d2);
     case GPK_MATERN12: {
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(KM_THREADS) kernel_matrix_kernel(const KmParam
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const bool same_pt = (r0 + ty * 4 + i) == (c0 + tx + 16 * j);
-          prod[i][j] *= eval_factor<T>(kind, d2[i][j], dt[i][j], same_pt, same_obj, d);
+          prod[i][j] *= eval_factor<T>(kind, d2[i][j], dt[i][j], same_pt, same_obj, d, p.desc.fac_param[f]);
         }
     }
 #pragma unroll
@@ -535,7 +539,7 @@ __global__ void kernel_diag_kernel(const KdParams p) {
         d2 = fma(df, df, d2);
         dt = fma(xr[k], yr[k], dt);
       }
-      prod *= eval_factor<T>(p.desc.fac_kind[f], d2, dt, true, p.same != 0, p.d);
+      prod *= eval_factor<T>(p.desc.fac_kind[f], d2, dt, true, p.same != 0, p.d, p.desc.fac_param[f]);
     }
     acc += prod;
   }

@@ -43,8 +43,15 @@ __device__ __forceinline__ T kb_sqrt(T v) {
 
 // value and derivative w.r.t. the squared distance (for LINEAR: value = dot, dval = 1 marks d/d(dot))
 template <typename T>
-__device__ __forceinline__ void eval_factor_grad(int kind, T d2, T dot, bool same_pt, int d, T& val, T& dval) {
+__device__ __forceinline__ void eval_factor_grad(int kind, T d2, T dot, bool same_pt, int d, T& val, T& dval, double param = 0.0) {
   switch (kind) {
+    case GPK_RQ: {  // v = (1 + d2 / (2 a))^-a ;  dv / d(d2) = -v / (2 (1 + d2 / (2 a)))
+      const double a = param, u = 1.0 + (double)d2 / (2.0 * a);
+      const double v = exp(-a * log(u));
+      val = (T)v;
+      dval = (T)(-0.5 * v / u);
+      return;
+    }
     case GPK_EQ: {
       val = kb_exp<T>(T(-0.5) * d2);
       dval = T(-0.5) * val;
@@ -152,7 +159,7 @@ __global__ void __launch_bounds__(KB_THREADS) kernel_matrix_bwd_kernel(const KbP
                 d2 = fma(df, df, d2);
                 dot = fma(xv, yv, dot);
               }
-              eval_factor_grad<T>(p.desc.fac_kind[f0 + q], d2, dot, same_pt, d, val[q], dval[q]);
+              eval_factor_grad<T>(p.desc.fac_kind[f0 + q], d2, dot, same_pt, d, val[q], dval[q], p.desc.fac_param[f0 + q]);
               prod *= val[q];
             }
           }

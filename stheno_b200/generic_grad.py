@@ -32,13 +32,14 @@ def kernel_needs_grad(k):
     for coef, fs in terms:
         if isinstance(coef, torch.Tensor) and coef.requires_grad:
             return True
-        for _, s in fs:
+        for f in fs:
+            s = f[1]
             if isinstance(s, torch.Tensor) and s.requires_grad:
                 return True
     return False
 
 
-def _factor(kind, xs, ys, elwise):
+def _factor(kind, xs, ys, elwise, param=None):
     if kind == "linear":
         return (xs * ys).sum(-1) if elwise else xs @ ys.transpose(-1, -2)
     if kind == "one":
@@ -62,7 +63,7 @@ def _factor(kind, xs, ys, elwise):
         s = math.sqrt(5.0) * r
         return (1 + s + 5.0 / 3.0 * d2) * torch.exp(-s)
     if kind == "rq":
-        raise NotImplementedError("rq handled by the caller (needs its alpha)")
+        return torch.exp(-param * torch.log1p(d2 / (2.0 * param)))
     raise NotImplementedError(f"no differentiable restatement of kernel kind {kind!r}")
 
 
@@ -75,9 +76,10 @@ def _eval(k, x, y, elwise):
     out = None
     for coef, fs in terms:
         t = None
-        for kind, s in fs:
+        for fac in fs:
+            kind, s = fac[0], fac[1]
             xs, ys = (x, y) if s is None else (x / _t(s, x), y / _t(s, y))
-            f = _factor(kind, xs, ys, elwise)
+            f = _factor(kind, xs, ys, elwise, fac[2] if len(fac) > 2 else None)
             t = f if t is None else t * f
         t = t * _t(coef, x)
         out = t if out is None else out + t

@@ -19,7 +19,7 @@ from ._lib import GpkError as _GpkError
 from ._util import batch_flatten, from_dev, origin_of, to_dev, uprank
 
 __all__ = [
-    "Kernel", "EQ", "Exp", "Matern12", "Matern32", "Matern52", "Linear", "Delta", "OneKernel", "ZeroKernel",
+    "Kernel", "EQ", "RQ", "Exp", "Matern12", "Matern32", "Matern52", "Linear", "Delta", "OneKernel", "ZeroKernel",
     "ScaledKernel", "SumKernel", "ProductKernel", "StretchedKernel", "ReversedKernel", "PosteriorKernel",
     "SubspaceKernel", "Mean", "ZeroMean", "OneMean", "ScaledMean", "SumMean", "ProductMean", "StretchedMean",
     "FunctionMean", "DerivativeMean", "DerivativeKernel", "PosteriorMean", "mean_var", "mean_var_diag", "num_elements", "pairwise", "elwise",
@@ -232,12 +232,13 @@ class Kernel:
         out, raw = [], []
         for coef, fs in terms:
             nf = []
-            for kind, s in fs:
+            for fac in fs:  # (kind, scale) or (kind, scale, shape parameter)
+                kind, s = fac[0], fac[1]
                 k = _scale_key(s)
                 if k not in keys:
                     keys[k] = len(scales)
                     scales.append(s)
-                nf.append((kind, keys[k]))
+                nf.append((kind, keys[k]) + tuple(fac[2:3]))
             out.append((float(coef.detach()) if isinstance(coef, torch.Tensor) else float(coef), nf))
             raw.append(coef)
         if not scales:
@@ -340,6 +341,23 @@ class Matern32(_Elementary):
 
 class Matern52(_Elementary):
     kind = "matern52"
+
+
+class RQ(_Elementary):
+    """Rational quadratic ``(1 + r^2 / (2 alpha))^-alpha`` (mlkernels ``RQ(alpha)``; ``README.md:1076-1088``)."""
+
+    kind = "rq"
+
+    def __init__(self, alpha):
+        self.alpha = float(alpha)
+        if not self.alpha > 0:
+            raise ValueError("RQ needs alpha > 0")
+
+    def flat_terms(self):
+        return [(1.0, [("rq", None, self.alpha)])]
+
+    def render(self):
+        return f"RQ({_fmt(self.alpha)})"
 
 
 class Linear(_Elementary):
@@ -520,7 +538,7 @@ class StretchedKernel(Kernel):
         t = self.k.flat_terms()
         if t is None:
             return None
-        return [(c, [(kind, _mul_scale(s, self.stretch_)) for kind, s in fs]) for c, fs in t]
+        return [(c, [(f[0], _mul_scale(f[1], self.stretch_)) + tuple(f[2:3]) for f in fs]) for c, fs in t]
 
     def _scaled_inputs(self, x, y, same):
         s = self.stretch_

@@ -78,7 +78,8 @@ class FlatKernel:
     ``terms`` is a list of ``(coef: float, [(kind: str, group: int), ...])``."""
 
     def __init__(self, terms, n_groups):
-        self.terms = [(float(c), [(str(k), int(g)) for k, g in fs]) for c, fs in terms]
+        # a factor is (kind, group) or (kind, group, param) -- param = the shape parameter of kinds that have one (rq: alpha)
+        self.terms = [(float(c), [tuple([str(f[0]), int(f[1])] + [float(v) for v in f[2:3]]) for f in fs]) for c, fs in terms]
         self.n_groups = max(int(n_groups), 1)
         if len(self.terms) > _lib.GPK_MAX_TERMS:
             raise GpkError(f"kernel expands to {len(self.terms)} product terms (limit {_lib.GPK_MAX_TERMS})")
@@ -95,9 +96,10 @@ class FlatKernel:
         for t, (coef, fs) in enumerate(self.terms):
             d.term_begin[t] = f
             d.coef[t] = coef
-            for kind, group in fs:
-                d.fac_kind[f] = KIND[kind]
-                d.fac_group[f] = group
+            for fac in fs:
+                d.fac_kind[f] = KIND[fac[0]]
+                d.fac_group[f] = fac[1]
+                d.fac_param[f] = fac[2] if len(fac) > 2 else 0.0
                 f += 1
         d.term_begin[len(self.terms)] = f
         return d
@@ -392,12 +394,12 @@ def _well_conditioned(flat, noise_scalar, noise_vec, jitter):
         return False
     scale = 0.0
     for coef, fs in flat.terms:
-        if any(kind == "linear" for kind, _ in fs):
+        if any(f[0] == "linear" for f in fs):
             return False
-        if all(kind == "delta" for kind, _ in fs):
+        if all(f[0] == "delta" for f in fs):
             continue  # a Delta term only adds to the diagonal
         scale += abs(coef)
-    diag = float(noise_scalar) + float(jitter) + sum(c for c, fs in flat.terms if fs and all(k == "delta" for k, _ in fs) and c > 0)
+    diag = float(noise_scalar) + float(jitter) + sum(c for c, fs in flat.terms if fs and all(f[0] == "delta" for f in fs) and c > 0)
     return diag >= 1e-3 * max(scale, 1e-300)
 
 

@@ -16,13 +16,15 @@ FlatKernel = real_ops.FlatKernel
 LOG_2_PI = math.log(2 * math.pi)
 
 
-def _factor(kind, x, y, same_obj):
+def _factor(kind, x, y, same_obj, param=None):
     # x: [B, n, d], y: [B, m, d]
     d = x.shape[-1]
     diff = x[:, :, None, :] - y[:, None, :, :]
     d2 = (diff * diff).sum(-1)
     if kind == "eq":
         return torch.exp(-0.5 * d2)
+    if kind == "rq":
+        return torch.exp(-param * torch.log1p(d2 / (2.0 * param)))
     if kind in ("matern12", "matern32", "matern52"):
         r = torch.sqrt(d2) if d == 1 else torch.sqrt(torch.clamp_min(d2, 1e-30))
         if kind == "matern12":
@@ -47,8 +49,8 @@ def _eval(flat, xg, yg, same):
     out = torch.zeros(xg.shape[1], xg.shape[2], yg.shape[2], dtype=xg.dtype)
     for coef, fs in flat.terms:
         prod = torch.full_like(out, coef)
-        for kind, g in fs:
-            prod = prod * _factor(kind, xg[g], yg[g], same)
+        for fac in fs:
+            prod = prod * _factor(fac[0], xg[fac[1]], yg[fac[1]], same, fac[2] if len(fac) > 2 else None)
         out = out + prod
     return out
 
@@ -100,7 +102,9 @@ def kernel_diag(flat, xg, yg=None, *, same=None):
     out = torch.zeros(B, n, dtype=xg.dtype)
     for coef, fs in flat.terms:
         prod = torch.full_like(out, coef)
-        for kind, g in fs:
+        for fac in fs:
+            kind, g = fac[0], fac[1]
+            param = fac[2] if len(fac) > 2 else None
             x, y = xg[g], yg[g]
             d2 = ((x - y) ** 2).sum(-1)
             if kind == "linear":
@@ -112,7 +116,7 @@ def kernel_diag(flat, xg, yg=None, *, same=None):
                 if v is None:
                     xx = x.reshape(-1, 1, x.shape[-1])
                     yy = y.reshape(-1, 1, y.shape[-1])
-                    v = _factor(kind, xx, yy, False).reshape(B, n)
+                    v = _factor(kind, xx, yy, False, param).reshape(B, n)
             prod = prod * v
         out = out + prod
     return out

@@ -526,3 +526,18 @@ def test_linear_kernel_stays_low_rank(S):
     # a sum with a dense kernel falls back to the dense path and still agrees
     g = S.GP(S.Linear() + S.EQ())
     approx(g(x, 0.3).logpdf(y), O.fdd_logpdf(("sum", ("linear",), ("eq",)), x, 0.3, y), rtol=1e-9)
+
+
+def test_rq_kernel(S):
+    # mlkernels RQ(alpha) (README.md:1076-1088): matrix, elwise, logpdf and posterior against the oracle, alone and composed
+    rng = np.random.default_rng(77)
+    x, xs = rng.standard_normal((30, 2)), rng.standard_normal((6, 2))
+    y = rng.standard_normal(30)
+    k = 1.5 * S.RQ(0.7).stretch(1.3) + S.EQ() * S.RQ(2.0)
+    spec = ("sum", ("scaled", 1.5, ("stretched", 1.3, ("rq", 0.7))), ("product", ("eq",), ("rq", 2.0)))
+    approx(S.B.dense(k(x, xs)), O.kernel_matrix(spec, x, xs), rtol=1e-11, atol=1e-13)
+    approx(k.elwise(x), O.kernel_elwise(spec, x), rtol=1e-11, atol=1e-13)
+    f = S.GP(k)
+    approx(f(x, 0.1).logpdf(y), O.fdd_logpdf(spec, x, 0.1, y), rtol=1e-10, atol=0)
+    approx((f | (f(x, 0.1), y))(xs).mean, O.posterior(spec, x, 0.1, y, xs)[0], rtol=1e-8, atol=1e-9)
+    assert str(S.RQ(0.5)) == "RQ(0.5)"
