@@ -196,7 +196,7 @@ class AbstractPseudoObservations(AbstractObservations):
         ch_A = A_mat.chol()
         half = ch_A.half_solve(prod.unsqueeze(1))  # [B, 1, m]  L_A^-1 prod
         sol = ch_A.full_solve(prod.unsqueeze(1))  # A^-1 prod
-        Lz_pad = torch.tril(ch_z.L_padded())  # zero strict upper triangle; identity on the padding
+        Lz_pad = ch_z.L_lower_()  # strict upper triangle zeroed in place (no copy); identity on the padding
         solp = torch.zeros(ch_z.batch, ops.TILE, m_pad, dtype=A.dtype, device=A.device)
         solp[:, :1, :m] = sol
         mu_rows = ops.gemm_nt(solp, Lz_pad)  # row 0 = (L_z A^-1 prod)^T

@@ -268,6 +268,14 @@ class Chol:
         """Dense ``[B, n, n]`` lower-triangular factor (copy; strict upper triangle zeroed)."""
         return torch.tril(self.W[:, : self.n, : self.n])
 
+    def L_lower_(self):
+        """The padded factor ``[B, n_pad, n_pad]`` with its strict upper triangle zeroed IN PLACE (no copy; done once): the
+        form products with ``L`` need (``L eps`` of sampling, ``L_z A L_z^T``).  Nothing else reads the upper triangle."""
+        if not getattr(self, "_upper_zeroed", False):
+            self.W[:, : self.n_pad, :].tril_()
+            self._upper_zeroed = True
+        return self.W[:, : self.n_pad, :]
+
     def rhs_half(self):
         """``(L^-1 rhs)^T`` for the fused right-hand sides: ``[B, k, n]`` (a view)."""
         return self.W[:, self.n_pad : self.n_pad + self.k, : self.n]

@@ -8,6 +8,7 @@ import torch
 
 from . import B
 from . import matrix as M
+from . import ops
 from ._util import NUMPY, batch_flatten, from_dev, origin_of, to_dev, uprank
 
 __all__ = ["Random", "RandomProcess", "RandomVector", "Normal"]
@@ -331,9 +332,14 @@ class Normal(RandomVector):
         elif isinstance(var, M.Zero):
             s = torch.zeros(bs + (n, num), dtype=var.dtype, device=var.device)
         else:
+            # mean + L eps with L read straight from the factorisation workspace by the in-tree tensor-core GEMM:
+            # (L eps)^T = eps^T L^T is an "NT" product with both operands K-contiguous (no tril copy, no library GEMM)
             ch = M.cholesky(var)
             eps = torch.randn((ch.batch, n, num), dtype=var.dtype, device=var.device, generator=state)
-            s = (ch.L() @ eps).reshape(bs + (n, num))
+            E = torch.zeros(ch.batch, ops.round_up(max(num, 1)), ch.n_pad, dtype=var.dtype, device=var.device)
+            E[:, :num, :n] = eps.transpose(1, 2)
+            St = ops.gemm_nt(E, ch.L_lower_())
+            s = St[:, :num, :n].transpose(1, 2).reshape(bs + (n, num))
         if not self.mean_is_zero:
             s = s + self._mean_dev()
         s = self._out(s)

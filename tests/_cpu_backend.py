@@ -177,6 +177,10 @@ class Chol:
     def L(self):
         return torch.tril(self.W[:, : self.n, : self.n])
 
+    def L_lower_(self):
+        self.W[:, : self.n_pad, :].tril_()
+        return self.W[:, : self.n_pad, :]
+
     def rhs_half(self):
         return self.W[:, self.n_pad : self.n_pad + self.k, : self.n]
 
@@ -299,9 +303,10 @@ def install(monkeypatch):
 
     import stheno_b200
     from stheno_b200 import _util, kernels, matrix
+    from stheno_b200 import random as random_mod
     from stheno_b200.model import observations
 
     me = sys.modules[__name__]
     monkeypatch.setattr(_util, "_device_fn", lambda: torch.device("cpu"))
-    for mod in (kernels, matrix, observations, stheno_b200):
+    for mod in (kernels, matrix, observations, random_mod, stheno_b200):
         monkeypatch.setattr(mod, "ops", me, raising=False)
