@@ -215,6 +215,21 @@ int gpk_transpose_f64(const double* src, int64_t lds, int64_t s_bstride, int64_t
 int gpk_transpose_f32(const float* src, int64_t lds, int64_t s_bstride, int64_t rows, int64_t cols, float* dst,
                       int64_t ldd, int64_t d_bstride, int32_t batch, void* stream);
 
+/* K3 in one call: posterior mean and marginal variance terms at m test points (PosteriorMean / PosteriorKernel behind
+ * stheno/model/observations.py:143-168, mlkernels.mean_var_diag via stheno/model/fdd.py:72-74), batch 1:
+ *   V^T = k(x*, x) L^-T (K1 rows + right TRSM);  dot[i] = <v_i, half_y>;  sq[i] = |v_i|^2
+ * half_y = (L^-1 (y - m(x)))^T zero-padded to n_pad (dot may be NULL: variance only; sq may be NULL: mean only).
+ * The caller adds the prior mean / subtracts sq from the prior variance.  Test points are processed in chunks of `chunk`
+ * rows (multiple of 128) through `ws` (>= chunk * n_pad elements, 16-byte aligned): K(x*, x) is never held whole. */
+int gpk_posterior_marginals_f64(const gpk_kernel_desc* desc_host, const double* xsg, int64_t xsg_gstride, int64_t m,
+                                const double* xg, int64_t xg_gstride, int64_t n, int32_t d, const double* L, int64_t ldl,
+                                int64_t n_pad, const double* half_y, double* dot, double* sq, int64_t chunk, double* ws,
+                                int64_t ws_elems, void* stream);
+int gpk_posterior_marginals_f32(const gpk_kernel_desc* desc_host, const float* xsg, int64_t xsg_gstride, int64_t m,
+                                const float* xg, int64_t xg_gstride, int64_t n, int32_t d, const float* L, int64_t ldl,
+                                int64_t n_pad, const float* half_y, float* dot, float* sq, int64_t chunk, float* ws,
+                                int64_t ws_elems, void* stream);
+
 /* Streamed sparse (inducing-point) accumulation -- AbstractPseudoObservations._compute, stheno/model/observations.py:279-336,
  * one chunk of `c` data points per call; K_zx (8.6 GB at n = 262144, m = 4096) is never held.  Per chunk, stream-ordered:
  *   W_c^T = k(x_c, z) L_z^-T  (:285, :301; rows = data points, [c_pad x m_pad], c_pad = round_up(c))

@@ -50,6 +50,8 @@ _SIGNATURES = {
     "gpk_pad_copy": [_ptr, _i64, _i64, _i64, _i64, _ptr, _i64, _i64, _i64, _i64, _f64, _i32, _i32, _ptr],
     "gpk_symmetrize": [_ptr, _i64, _i64, _i64, _i32, _ptr],
     "gpk_transpose": [_ptr, _i64, _i64, _i64, _i64, _ptr, _i64, _i64, _i32, _ptr],
+    "gpk_posterior_marginals": [POINTER(KernelDesc), _ptr, _i64, _i64, _ptr, _i64, _i64, _i32, _ptr, _i64, _i64, _ptr, _ptr, _ptr,
+                                _i64, _ptr, _i64, _ptr],
     "gpk_sparse_accumulate": [POINTER(KernelDesc), _ptr, _i64, _i64, _ptr, _i64, _i64, _i32, _ptr, _i64, _i64, _ptr, _ptr, _ptr,
                               _i32, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _ptr],
 }

@@ -1322,10 +1322,18 @@ def mean_var_diag(mean, kernel, x):
     ``V = k(x*, z) L^-T`` (``stheno/model/fdd.py:72-74``; call pattern pinned by ``tests/model/test_model.py:335-365``)."""
     if _shared_posterior(mean, kernel) and not _is_multi(x):
         ch = kernel.K_z.chol()
-        V, m = kernel._half(kernel.k_zi, x)
-        dot, sq = ops.row_dot_sq(V, m, ch.n_pad, mean._half_y())
         prior_m = mean.m_i.dev(x)
         prior_v = _elwise_any(kernel.k_ij, x, None, True)
         shp = prior_m.shape[:-1]
+        flat, scales = (None, None)
+        if ch.batch == 1 and not _is_multi(kernel.z) and kernel.k_zi.symmetric:
+            flat, scales = kernel.k_zi._flat()
+        xi, zi = as_input(x), (as_input(kernel.z) if flat is not None else None)
+        if flat is not None and flat.terms and not xi.batch_shape and not zi.batch_shape:
+            # K3 in ONE call: kernel rows -> tensor-core solve -> both reductions, test points streamed through a bounded buffer
+            dot, sq = ops.posterior_marginals(flat, xi.scaled(scales), zi.scaled(scales), ch, mean._half_y()[0])
+        else:
+            V, m = kernel._half(kernel.k_zi, x)
+            dot, sq = ops.row_dot_sq(V, m, ch.n_pad, mean._half_y())
         return prior_m + dot.reshape(shp).unsqueeze(-1), prior_v - sq.reshape(shp).unsqueeze(-1)
     return mean.dev(x), _elwise_any(kernel, x, None, True)

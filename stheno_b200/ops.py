@@ -507,6 +507,39 @@ def kernel_rows_padded(flat, xsg, xg, chol):
     return out
 
 
+def posterior_marginals(flat, xsg, xg, chol, half_y=None, want_sq=True, chunk=4096):
+    """K3 in one call (``gpk_posterior_marginals``): ``(dot [m], sq [m])`` with ``V^T = k(x*, x) L^-T``, ``dot = V^T half_y``,
+    ``sq = |v_i|^2``; one problem (no batch), test points streamed in chunks of ``chunk`` rows."""
+    _check_groups(xg, flat)
+    _require_cuda(xsg, xg, half_y)
+    if chol.batch != 1 or xsg.shape[1] != 1 or xg.shape[1] != 1:
+        raise ValueError("posterior_marginals handles a single problem")
+    xsg, xg = xsg.contiguous(), xg.contiguous()
+    m, d = xsg.shape[2], xsg.shape[3]
+    dt, dev = chol.dtype, chol.device
+    dot = torch.empty(m, dtype=dt, device=dev) if half_y is not None else None
+    sq = torch.empty(m, dtype=dt, device=dev) if want_sq else None
+    if m == 0:
+        return dot, sq
+    chunk = min(round_up(chunk), round_up(m))
+    ws = torch.empty(chunk * chol.n_pad, dtype=dt, device=dev)
+    if dt == torch.float64:  # the solve's largest product: rows x n/2 x n/2
+        h = round_up(chol.n_pad // 2)
+        slices = _oz_slices(False)
+        need = _lib.load().gpk_f64_emulation_scratch_bytes(chunk, chol.n_pad - h + TILE, h, slices) if (
+            slices and chunk * (chol.n_pad - h + TILE) * h >= 1.5e9) else 0
+        _set_emulation(dev, slices, need)
+    Lp = chol.L_padded()
+    hy = None if half_y is None else half_y.contiguous()
+    desc = flat.desc()
+    rc = _fn("gpk_posterior_marginals", dt)(
+        ctypes.byref(desc), _ptr(xsg), xsg.stride(0), m, _ptr(xg), xg.stride(0), xg.shape[2], d, _ptr(Lp), Lp.stride(1),
+        chol.n_pad, _ptr(hy), _ptr(dot), _ptr(sq), chunk, _ptr(ws), ws.numel(), _stream(),
+    )
+    check(rc, "gpk_posterior_marginals")
+    return dot, sq
+
+
 SPARSE_METHOD = {"vfe": 0, "fitc": 1, "dtc": 2}
 
 

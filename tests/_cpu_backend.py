@@ -260,6 +260,15 @@ def kernel_rows_padded(flat, xsg, xg, chol):
     return out
 
 
+def posterior_marginals(flat, xsg, xg, chol, half_y=None, want_sq=True, chunk=4096):
+    V = kernel_rows_padded(flat, xsg, xg, chol)
+    chol.solve_rows_(V)
+    m = xsg.shape[2]
+    dot = (V[0, :m] * half_y[None, :]).sum(-1) if half_y is not None else None
+    sq = (V[0, :m] ** 2).sum(-1) if want_sq else None
+    return dot, sq
+
+
 class SparseAccumulator:
     """torch-CPU stand-in of ``ops.SparseAccumulator`` (same interface and accumulation semantics, chunk by chunk)."""
 
