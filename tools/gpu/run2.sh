@@ -35,3 +35,21 @@ e1.record(); torch.cuda.synchronize()
 print("NB_OUTER", os.environ["GPK_NB_OUTER"], "logpdf ms", e0.elapsed_time(e1) / 10, float(lp))
 P
 done
+echo "== C3 knobs (64 x 2048 fp32, ms per batched logpdf)"
+for cfg in "GPK_NB_OUTER=512" "GPK_NB_OUTER=256" "GPK_NB_OUTER=1024" "GPK_NO_LOOKAHEAD=1" "GPK_NB_OUTER=256 GPK_NO_LOOKAHEAD=1"; do
+env $cfg timeout 200 python - "$cfg" <<'P'
+import sys, torch
+sys.path.insert(0, ".")
+import stheno_b200 as S
+S.B.epsilon = 1e-6
+g = torch.Generator(device="cuda").manual_seed(3)
+for Bn in (64, 512):
+    x = torch.randn(Bn, 2048, 8, device="cuda", generator=g); y = torch.randn(Bn, 2048, 1, device="cuda", generator=g)
+    for _ in range(3): lp = S.GP(S.EQ())(x, 0.1).logpdf(y)
+    torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): lp = S.GP(S.EQ())(x, 0.1).logpdf(y)
+    e1.record(); torch.cuda.synchronize()
+    print(sys.argv[1], "B", Bn, "ms", e0.elapsed_time(e1) / 5, float(lp.sum()))
+P
+done
