@@ -189,6 +189,8 @@ def gemm_nt(A, Bm, C=None, *, alpha=1.0, beta=0.0, lower=False):
 
 
 def _pad_copy(src, dst, rows, cols, rows_pad, cols_pad, diag_add, pad_identity):
+    if src.stride(2) != 1:
+        src = src.contiguous()
     rc = _fn("gpk_pad_copy", dst.dtype)(
         _ptr(src), src.stride(1), src.stride(0), rows, cols, _ptr(dst), dst.stride(1), dst.stride(0), rows_pad,
         cols_pad, float(diag_add), 1 if pad_identity else 0, dst.shape[0], _stream(),
@@ -205,6 +207,8 @@ def symmetrize_(A, n):
 
 def transpose(src, rows, cols, out=None):
     """``out[B, cols, rows] = src[B, rows, cols]^T`` (leading block of possibly padded tensors)."""
+    if src.stride(2) != 1:  # a transposed VIEW (e.g. a reversed cross-kernel): the kernels take a unit inner stride
+        src = src.contiguous()
     if out is None:
         out = torch.empty(src.shape[0], cols, rows, device=src.device, dtype=src.dtype)
     rc = _fn("gpk_transpose", src.dtype)(
@@ -217,6 +221,8 @@ def transpose(src, rows, cols, out=None):
 
 def row_dot_sq(V, rows, n_cols, b=None, want_dot=True, want_sq=True):
     """Per-row ``<V[r, :n_cols], b>`` and ``|V[r, :n_cols]|^2`` of ``V[B, *, *]`` -> two ``[B, rows]`` tensors."""
+    if V.stride(2) != 1:
+        V = V.contiguous()
     Bn = V.shape[0]
     dot = torch.empty(Bn, rows, device=V.device, dtype=V.dtype) if (want_dot and b is not None) else None
     sq = torch.empty(Bn, rows, device=V.device, dtype=V.dtype) if want_sq else None
