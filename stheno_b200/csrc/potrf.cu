@@ -218,14 +218,12 @@ potrf_leaf_rec_kernel(T* __restrict__ A, int64_t lda, int64_t a_bs, T* __restric
   for (int b = 0; b < 4; ++b) {
     // ---- S0: warp 0 factorises A_bb; the other warps finish the rank-32 update of step b - 1 (blocks right of column b)
     if (warp == 0) {
-      // In-register factorisation of the 32 x 32 block, lane = row, in the SQUARE-ROOT-FREE form: column j is kept
-      // UNSCALED (b_ij) while the block is eliminated, a_ik -= (b_ij / d_j) b_kj, and scaled by 1 / sqrt(d_k) once at the
-      // end.  What this buys: the broadcast of column j through shared memory (STS -> warp barrier -> LDS) no longer waits
-      // for the pivot's reciprocal square root -- it is issued as soon as column j is final, one step ahead, and runs
-      // concurrently with the pivot chain  shuffle(d_j) -> reciprocal -> multiply -> FMA on the next pivot,  which is all
-      // that remains serial per column (a fast reciprocal: MUFU seed + two Newton steps, instead of rsqrt + its fix-ups).
+      // (A square-root-free variant -- columns kept unscaled, broadcast one step ahead of the pivot chain, MUFU reciprocal
+      //  + two Newton steps -- was built and measured in round 2: 32.7 us per leaf against 33.1 us for this form, i.e. the
+      //  column chain is not what bounds the leaf any more; it also moved the last digits of the reference's README
+      //  regression G1 (condition number ~1e16) outside its 5e-6 window, so the Cholesky form below stays.)
       double a[32];
-      double dd = 1.0;
+      double diag_l = 1.0;
       const double* row = S + (32 * b + lane) * RL_LD + 32 * b;
 #pragma unroll
       for (int k = 0; k < 32; k += 2) {
@@ -233,36 +231,22 @@ potrf_leaf_rec_kernel(T* __restrict__ A, int64_t lda, int64_t a_bs, T* __restric
         a[k] = v.x;
         a[k + 1] = v.y;
       }
-      colT[lane] = a[0];
-      __syncwarp();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const double d = __shfl_sync(0xffffffffu, a[j], j);
         if (lane == 0 && !(d > 0.0)) atomicCAS(info + bidx, 0, pivot_base + 32 * b + j + 1);
-        if (lane == j) dd = d;
-        double r;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-        r = fma(r, fma(-d, r, 1.0), r);
-        r = fma(r, fma(-d, r, 1.0), r);
-        const double t = a[j] * r;
-#pragma unroll
-        for (int k = j + 1; k < 32; ++k) a[k] = fma(-t, colT[j * 32 + k], a[k]);  // b_kj: loads independent of the pivot
-        if (j < 31) {
-          colT[(j + 1) * 32 + lane] = a[j + 1];  // column j + 1 is final now: broadcast it one step ahead
-          __syncwarp();
+        const double inv = rsqrt(d);
+        const double l = a[j] * inv;  // lane j: sqrt(d); lanes > j: L[lane][j]; lanes < j: unused
+        colT[j * 32 + lane] = l;
+        if (lane == j) {
+          dinv[j] = inv;
+          diag_l = l;
         }
+        __syncwarp();
+#pragma unroll
+        for (int k = j + 1; k < 32; ++k) a[k] = fma(-l, colT[j * 32 + k], a[k]);
+        a[j] = l;
       }
-      // scale: L_ik = b_ik / sqrt(d_k); lane k owns d_k
-      const double sc = rsqrt(dd);
-      __syncwarp();
-      dinv[lane] = sc;  // 1 / L_kk
-      __syncwarp();
-#pragma unroll
-      for (int k = 0; k < 32; ++k) a[k] *= dinv[k];
-      __syncwarp();
-#pragma unroll
-      for (int k = 0; k < 32; ++k) colT[k * 32 + lane] = a[k];  // colT[j][i] = L[i][j] for the solves of S1 (i > j entries valid)
-      const double diag_l = dd * sc;
       double* out = S + (32 * b + lane) * RL_LD + 32 * b;
 #pragma unroll
       for (int k = 0; k < 32; ++k)
