@@ -264,6 +264,10 @@ void gpk_gemm_profile_enable(int32_t on);
 int gpk_gemm_profile_read_kind(int32_t kind, double* total_ms, double* total_flops, int64_t* launches); /* 0 DMMA, 1 int8 emulation, -1 all */
 int gpk_gemm_profile_read(double* total_ms_host, double* total_flops_host, int64_t* launches_host);
 
+/* Measurement helper (tools/time_leaf_phases.py): while `buf` (>= 16 int64, device memory) is set, every leaf-Cholesky launch
+ * records clock64() at its phase boundaries there; NULL switches it off.  Synchronises the device. */
+int gpk_debug_leaf_phase_clock(void* buf16_int64);
+
 /* Number of kernels this library has launched since load / the last reset (bench.py's `gpu_launches`). */
 int64_t gpk_launch_count(void);
 void gpk_launch_count_reset(void);

@@ -184,6 +184,10 @@ __device__ __forceinline__ void rl_update_cols(double* S, int r, int c, int b, i
   }
 }
 
+// measurement helper (tools/time_leaf_phases.py): when set, thread 0 of every leaf launch writes clock64() at its phase
+// boundaries (start, loaded, then S0 / S1 / S2 of each 32-block, end) into this buffer
+__device__ long long* g_leaf_phase_clock = nullptr;
+
 template <typename T>
 __global__ void __launch_bounds__(RL_THREADS, 1)
 potrf_leaf_rec_kernel(T* __restrict__ A, int64_t lda, int64_t a_bs, T* __restrict__ logdet, int32_t* __restrict__ info,
@@ -195,6 +199,9 @@ potrf_leaf_rec_kernel(T* __restrict__ A, int64_t lda, int64_t a_bs, T* __restric
   const int bidx = blockIdx.x;
   A += (int64_t)bidx * a_bs;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  long long* const dbg = (tid == 0 && bidx == 0) ? g_leaf_phase_clock : nullptr;
+  int dbg_i = 0;
+  if (dbg) dbg[dbg_i++] = clock64();
 
   // ---- load the lower triangle (granules of two columns; the granule that straddles the diagonal is loaded whole)
   for (int gi = tid; gi < NB * NB / 2; gi += RL_THREADS) {
@@ -212,6 +219,7 @@ potrf_leaf_rec_kernel(T* __restrict__ A, int64_t lda, int64_t a_bs, T* __restric
     }
   }
   __syncthreads();
+  if (dbg) dbg[dbg_i++] = clock64();
 
   double logsum = 0.0;  // warp 0 only
 #pragma unroll 1
@@ -269,6 +277,7 @@ potrf_leaf_rec_kernel(T* __restrict__ A, int64_t lda, int64_t a_bs, T* __restric
       }
     }
     __syncthreads();
+    if (dbg) dbg[dbg_i++] = clock64();
     if (b == 3) break;
     // ---- S1: rows below the diagonal block: x L_bb^T = a, one thread per row
     const int nrows = NB - 32 * (b + 1);
@@ -291,12 +300,14 @@ potrf_leaf_rec_kernel(T* __restrict__ A, int64_t lda, int64_t a_bs, T* __restric
       for (int k = 0; k < 32; k += 2) *reinterpret_cast<double2*>(rowp + k) = make_double2(x[k], x[k + 1]);
     }
     __syncthreads();
+    if (dbg) dbg[dbg_i++] = clock64();
     // ---- S2: rank-32 update of block column b + 1 (blocks (r, b + 1), r = b + 1..3), units of 2 columns over all warps
     {
       const int c = b + 1;
       for (int u = warp; u < (4 - c) * 16; u += RL_WARPS) rl_update_cols(S, c + (u >> 4), c, b, 2 * (u & 15), 2 * (u & 15) + 2, lane);
     }
     __syncthreads();
+    if (dbg) dbg[dbg_i++] = clock64();
   }
 
   // ---- store the lower triangle
@@ -317,6 +328,7 @@ potrf_leaf_rec_kernel(T* __restrict__ A, int64_t lda, int64_t a_bs, T* __restric
     const double s = warp_sum(logsum);
     if (lane == 0) atomicAdd(logdet + bidx, (T)(2.0 * s));
   }
+  if (dbg) dbg[dbg_i++] = clock64();
 }
 
 // ---- leaf TRSM:  X L^T = B  (B: rows x 128, 64 rows per CTA), in place ----------------------------------------
@@ -1019,6 +1031,11 @@ static int trsm_right_t_driver(const T* L, int64_t ldl, int64_t l_bs, int64_t n_
 }  // namespace gpk
 
 extern "C" {
+int gpk_debug_leaf_phase_clock(void* buf16_int64) {
+  long long* p = static_cast<long long*>(buf16_int64);
+  cudaError_t e = cudaMemcpyToSymbol(gpk::g_leaf_phase_clock, &p, sizeof(p));
+  return e == cudaSuccess ? 0 : -1000 - (int)e;
+}
 int64_t gpk_potrf_oz_ws_bytes(int64_t n_pad, int64_t extra_rows, int32_t slices) {
   return gpk::oz_ws_bytes(n_pad + extra_rows, gpk::nb_outer(), slices);
 }

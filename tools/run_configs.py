@@ -62,7 +62,9 @@ if "c4" in which:
     f = S.GP(S.Matern52().stretch(2.0))
     def elbo():
         return S.PseudoObs(f(z), f(x, 0.1), y).elbo(f.measure)
+    torch.cuda.reset_peak_memory_stats()
     t, e = ev(elbo, reps=2)
+    res["c4_peak_mem_gb"] = torch.cuda.max_memory_allocated() / 1e9
     res["c4_elbo_ms"] = t; res["c4_elbo"] = float(e); res["c4_tflops"] = (2.0 * m * m * n + 2 * m**3 / 3) / t / 1e9
     del x, y, z
     torch.cuda.empty_cache()
@@ -97,4 +99,4 @@ if "c5" in which:
     res["c5_loss_and_grad_N32768_ms"] = t; res["c5_loss"] = float(l)
     res["c5_grad_H_norm"] = float(H.grad.norm()); res["c5_peak_mem_gb"] = torch.cuda.max_memory_allocated() / 1e9
 print(json.dumps(res, indent=1))
-import os; os.makedirs("gpurun_out", exist_ok=True); json.dump(res, open("gpurun_out/configs.json", "w"), indent=1)
+import os; os.makedirs("gpurun_out", exist_ok=True); json.dump(res, open("gpurun_out/r02_configs.json", "w"), indent=1)
