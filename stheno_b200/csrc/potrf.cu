@@ -203,20 +203,24 @@ potrf_leaf_rec_kernel(T* __restrict__ A, int64_t lda, int64_t a_bs, T* __restric
   int dbg_i = 0;
   if (dbg) dbg[dbg_i++] = clock64();
 
-  // ---- load the lower triangle (granules of two columns; the granule that straddles the diagonal is loaded whole)
+  // ---- load the lower triangle (granules of two columns; the granule that straddles the diagonal is loaded whole).
+  // fp64: straight global -> shared copies (cp.async, all ~11 granules of a thread in flight at once: the staged
+  // register loop took 4.8k cycles, a quarter of it latency the copies now overlap)
   for (int gi = tid; gi < NB * NB / 2; gi += RL_THREADS) {
     const int row = gi >> 6, k = (gi & 63) * 2;
     if (k <= row) {
       const T* src = A + (int64_t)row * lda + k;
-      double2 v;
       if (sizeof(T) == 8) {
-        v = *reinterpret_cast<const double2*>(src);
+        cp_async16(S + row * RL_LD + k, src);
       } else {
         const float2 f = *reinterpret_cast<const float2*>(src);
-        v = make_double2((double)f.x, (double)f.y);
+        *reinterpret_cast<double2*>(S + row * RL_LD + k) = make_double2((double)f.x, (double)f.y);
       }
-      *reinterpret_cast<double2*>(S + row * RL_LD + k) = v;
     }
+  }
+  if (sizeof(T) == 8) {
+    cp_async_commit();
+    cp_async_wait<0>();
   }
   __syncthreads();
   if (dbg) dbg[dbg_i++] = clock64();
@@ -261,19 +265,26 @@ potrf_leaf_rec_kernel(T* __restrict__ A, int64_t lda, int64_t a_bs, T* __restric
         if (k <= lane) out[k] = a[k];
       logsum += log(diag_l);
     } else if (b > 0) {
-      // blocks (r, c), b + 1 <= c <= r <= 3, updated with block column b - 1: units of 4 columns over warps 1..RL_WARPS-1
+      // blocks (r, c), b + 1 <= c <= r <= 3, updated with block column b - 1.  ONE unit per warp, as many columns as that
+      // takes: every unit re-reads its 32 x 32 row operand from shared memory (64 wavefronts), and with 2-4 column units
+      // that re-read made these updates shared-memory-bandwidth bound (phase clocks, round 2: 7.1k cycles for 3 blocks
+      // whose 98k FMAs need 1.5k) -- so the column ranges are as wide as the warp count allows.
       const int pb = b - 1;
       const int nblk = (4 - b) * (3 - b) / 2;  // b = 1: (2,2) (3,2) (3,3) ; b = 2: (3,3) ; b = 3: none
-      for (int u = warp - 1; u < nblk * 8; u += RL_WARPS - 1) {
-        const int blk = u >> 3, q = u & 7;
-        int r, c;
-        if (b == 1) {
-          c = (blk == 2) ? 3 : 2;
-          r = (blk == 0) ? 2 : 3;
-        } else {
-          r = c = 3;
+      if (nblk > 0) {
+        const int U = (RL_WARPS - 1) / nblk;  // units per block
+        const int u = warp - 1;
+        if (u < U * nblk) {
+          const int blk = u / U, q = u - blk * U;
+          int r, c;
+          if (b == 1) {
+            c = (blk == 2) ? 3 : 2;
+            r = (blk == 0) ? 2 : 3;
+          } else {
+            r = c = 3;
+          }
+          rl_update_cols(S, r, c, pb, (q * 32) / U, ((q + 1) * 32) / U, lane);
         }
-        rl_update_cols(S, r, c, pb, 4 * q, 4 * q + 4, lane);
       }
     }
     __syncthreads();
@@ -301,10 +312,13 @@ potrf_leaf_rec_kernel(T* __restrict__ A, int64_t lda, int64_t a_bs, T* __restric
     }
     __syncthreads();
     if (dbg) dbg[dbg_i++] = clock64();
-    // ---- S2: rank-32 update of block column b + 1 (blocks (r, b + 1), r = b + 1..3), units of 2 columns over all warps
+    // ---- S2: rank-32 update of block column b + 1 (blocks (r, b + 1), r = b + 1..3): one unit per warp (see S0)
     {
-      const int c = b + 1;
-      for (int u = warp; u < (4 - c) * 16; u += RL_WARPS) rl_update_cols(S, c + (u >> 4), c, b, 2 * (u & 15), 2 * (u & 15) + 2, lane);
+      const int c = b + 1, nblk = 4 - c, U = RL_WARPS / nblk;
+      if (warp < U * nblk) {
+        const int blk = warp / U, q = warp - blk * U;
+        rl_update_cols(S, c + blk, c, b, (q * 32) / U, ((q + 1) * 32) / U, lane);
+      }
     }
     __syncthreads();
     if (dbg) dbg[dbg_i++] = clock64();
