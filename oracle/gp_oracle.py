@@ -408,38 +408,53 @@ def sparse_compute(spec, z, x, noise_diag, y, method="vfe", noise_z=None, mean_x
     return {"K_z": K_z, "A": A_store, "mu": mu, "elbo": float(elbo), "L_z": L_z}
 
 
-def sparse_compute_chunked(spec, z, x, noise_diag, y, method="vfe", noise_z=None, chunk=16384, eps=EPSILON):
+def sparse_compute_chunked(spec, z, x, noise_diag, y, method="vfe", noise_z=None, chunk=16384, eps=EPSILON, workers=1):
     """:func:`sparse_compute` (``observations.py:279-336``, zero means) evaluated over column chunks of ``K_zx`` so that
     the full-size configuration (n = 262144, m = 4096: ``K_zx`` = 8.6 GB, several temporaries of that size in the plain
     restatement) fits a test host.  Every line is the same arithmetic restricted to the data points of one chunk; the
-    sums over data points (``A``, ``prod``, the scalars) are accumulated chunk by chunk.  Checked against
-    :func:`sparse_compute` in ``tests/test_oracle_golden.py``.  Returns ``elbo``, ``mu`` and ``A`` (= ``L_z A L_z^T``)."""
+    sums over data points (``A``, ``prod``, the scalars) are accumulated chunk by chunk (``workers`` > 1: chunks are
+    evaluated by a thread pool -- NumPy releases the GIL in its element-wise passes -- and summed in chunk order).
+    Checked against :func:`sparse_compute` in ``tests/test_oracle_golden.py``.  Returns ``elbo``, ``mu``, ``A`` (= ``L_z A L_z^T``)."""
     z, x = np.asarray(z, np.float64), np.asarray(x, np.float64)
     y = _uprank(np.asarray(y, np.float64))
     n, m = x.shape[0], z.shape[0]
     K_z = kernel_matrix(spec, z) + noise_matrix(noise_z, m)  # :286
     L_z = chol_eps(K_z, eps)  # :300
     K_n_all = np.broadcast_to(np.asarray(noise_diag, np.float64), (n,))
-    A = np.eye(m)
-    prod = np.zeros((m, 1))
-    log_kn = yky = trace_part = 0.0
-    for a in range(0, n, chunk):
+    if method not in ("vfe", "fitc", "dtc"):
+        raise ValueError(method)
+
+    def one(a):
         xc, yc = x[a : a + chunk], y[a : a + chunk]
         K_n = K_n_all[a : a + chunk].copy()  # :290
         W = _tri(L_z, kernel_matrix(spec, z, xc))  # :285, :301
+        trace = 0.0
         if method in ("vfe", "fitc"):
             corr = kernel_elwise(spec, xc)[:, 0] - np.sum(W * W, axis=0)  # :304-306
-        if method == "vfe":
-            trace_part += np.sum(corr / K_n)  # :308-310
-        elif method == "fitc":
-            K_n = K_n + corr  # :311-313
-        elif method != "dtc":
-            raise ValueError(method)
+            if method == "vfe":
+                trace = np.sum(corr / K_n)  # :308-310
+            else:
+                K_n = K_n + corr  # :311-313
         Ws = W / K_n
-        A += Ws @ W.T  # :322
-        prod += Ws @ yc  # :327
-        log_kn += np.sum(np.log(2 * np.pi * K_n))
-        yky += np.sum(yc[:, 0] ** 2 / K_n)
+        return Ws @ W.T, Ws @ yc, np.sum(np.log(2 * np.pi * K_n)), np.sum(yc[:, 0] ** 2 / K_n), trace  # :322, :327, :334, :335
+
+    starts = list(range(0, n, chunk))
+    if workers > 1:
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            parts = list(pool.map(one, starts))
+    else:
+        parts = [one(a) for a in starts]
+    A = np.eye(m)
+    prod = np.zeros((m, 1))
+    log_kn = yky = trace_part = 0.0
+    for dA, dp, dl, dy, dt in parts:
+        A += dA
+        prod += dp
+        log_kn += dl
+        yky += dy
+        trace_part += dt
     L_A = chol_eps(A, eps)
     mu = L_z @ sla.cho_solve((L_A, True), prod)  # :329
     t = _tri(L_A, prod)
