@@ -381,6 +381,26 @@ def _potrf(W, n, n_pad, extra, k, well_conditioned=False):
     return Chol(W, n, k, logdet, info)
 
 
+_PRODUCT_SLICES_AUTO = [8]
+
+
+class product_slices:
+    """``with ops.product_slices(7): ...`` -- inside the block, ``B.precision = "auto"`` emulates the large products and solves
+    with that many int8 slices instead of 8.  For consumers with a looser accuracy target than the 1e-10 parity bar of
+    log-pdfs and posteriors: the analytic backward pass (hyper-parameter gradients, checked at 1e-8) forms ``K^-1`` from one
+    big solve and one big product, 1.3x faster with 7 slices."""
+
+    def __init__(self, slices):
+        self.slices = int(slices)
+
+    def __enter__(self):
+        self.prev = _PRODUCT_SLICES_AUTO[0]
+        _PRODUCT_SLICES_AUTO[0] = self.slices
+
+    def __exit__(self, *exc):
+        _PRODUCT_SLICES_AUTO[0] = self.prev
+
+
 def _oz_slices(well_conditioned=False):
     """``B.precision`` -> number of int8 slices of the emulated large fp64 updates (0: native fp64 tensor cores only).
 
@@ -397,7 +417,7 @@ def _oz_slices(well_conditioned=False):
 
     mode = getattr(_Bns, "precision", "auto")
     if mode == "auto":
-        return 7 if well_conditioned else 8
+        return 7 if well_conditioned else _PRODUCT_SLICES_AUTO[0]
     return {"int8x5": 5, "int8x6": 6, "int8x7": 7, "int8x8": 8}.get(mode, 0)
 
 
