@@ -438,7 +438,8 @@ int oz_launch_gemm(int64_t M, int64_t N, int64_t K, double alpha, const int8_t* 
   const int32_t total = lower ? tri_rows * (tri_rows + 1) + (tiles_m - tri_rows) * tiles_n : tiles_m * tiles_n;
   static const int force_tpc = getenv("GPK_OZ_TPC") ? atoi(getenv("GPK_OZ_TPC")) : 0;
   int32_t tpc = force_tpc > 0 ? force_tpc : total / 296;  // >= 2 waves of CTAs over 148 SMs before CTAs grow
-  tpc = tpc < 1 ? 1 : (tpc > 4 && force_tpc <= 0 ? 4 : tpc);
+  const int32_t tpc_cap = K > 512 ? 2 : 4;  // CTAs stay short-lived (look-ahead streams need SMs every few tens of us)
+  tpc = tpc < 1 ? 1 : (tpc > tpc_cap && force_tpc <= 0 ? tpc_cap : tpc);
   OzParams p{alpha, C, scA + rowA, scB + rowB, ldc, (int32_t)rowA, (int32_t)rowB, (int32_t)(K / OZ_BK), lower,
              tiles_m, tiles_n, total, tpc, tri_rows, beta != 0.0 ? 1 : 0};
   // profile: algorithmic (fp64-equivalent) flops of the tiles computed; the int8 work is S (S + 1) / 2 times that

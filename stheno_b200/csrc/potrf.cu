@@ -838,6 +838,10 @@ int oz_gemm_sliced(int64_t, int64_t, int64_t, double, const void*, int64_t, int6
 //   MODE_TF32X3  opt-in: fp32 copy of the panel, 3xTF32 products on tcgen05 (fp32-level products)
 //   MODE_OZAKI   int8 slices of the panel (error-free split), exact int32 products on tcgen05, fp64 recombination
 enum { MODE_F64 = 0, MODE_TF32X3 = 1, MODE_OZAKI = 2 };
+// scratch of the pair scheme: the pair's rows sliced 1024 wide + one panel's rows sliced 512 wide
+static inline int64_t potrf_pairs_ws_bytes(int64_t R, int32_t S) {
+  return ((oz_ws_bytes(R, 1024, S) + 1023) & ~int64_t(1023)) + oz_ws_bytes(R, 512, S);
+}
 struct Trailing {
   int mode = MODE_F64;
   void* ws = nullptr;
@@ -888,6 +892,69 @@ int trailing_update<double>(int used, const Trailing& t, int64_t rA, int64_t rB,
   return gemm_nt(M, N, K, -1.0, PA, lda, a_bs, PB, lda, a_bs, 1.0, C, lda, a_bs, lower, batch, stream);
 }
 
+// ---- fp64 + int8 emulation, single matrix: outer panels factorised in PAIRS ------------------------------------------
+// The emulated update drains S x 64 TMEM columns per 128 x 64 tile whatever K is (25 % of a tile's MMA time at K = 512,
+// 12 % at K = 1024), and every outer step reads and writes the whole trailing matrix once.  Widening the outer panel to
+// 1024 directly was measured slower (the 128-wide leaf steps then push twice the rank-128 DMMA updates through the panel).
+// Here the 512-wide panels keep their leaf steps, but the FAR part of the trailing matrix is updated once per PAIR of
+// panels with K = 1024 (the pair's rows re-sliced as one 1024-wide operand), i.e. half the passes over the trailing
+// matrix and half the accumulator drains per flop:
+//   pair (A, B) factorised  ->  X = slices of rows below x [A | B]  (K = 1024)
+//   side streams: block column A' of the next pair  -= X X^T ; factor A' ; Y = slices of rows below x A' (K = 512) ;
+//                 block column B' -= X X^T (bulk stream, any time) and -= Y Y^T (after it) ; factor B'
+//   caller's stream: everything right of the next pair -= X X^T (K = 1024), concurrently.
+// Updates that touch the same block are ordered by streams / events (never concurrent: results stay bit-reproducible).
+static int potrf_driver_pairs(double* A, int64_t lda, int64_t n_pad, int64_t extra_rows, double* logdet, int32_t* info,
+                              cudaStream_t stream, void* ws, int32_t S, Lookahead& la) {
+  auto ce = [](cudaError_t e) { return e == cudaSuccess ? 0 : -1000 - (int)e; };
+  const int64_t R = n_pad + extra_rows, P = 512;
+  void* wsX = ws;                                                                       // [S][R][1024] + scales
+  void* wsY = static_cast<char*>(ws) + ((oz_ws_bytes(R, 2 * P, S) + 1023) & ~int64_t(1023));  // [S][R][512] + scales
+  int rc;
+  auto upd = [&](void* w, int64_t K, int64_t rA, int64_t rB, int64_t M, int64_t N, double* C, int32_t lower,
+                 cudaStream_t s) -> int {
+    if (M <= 0 || N <= 0) return 0;
+    return oz_gemm_sliced(M, N, K, -1.0, w, R, rA, w, R, rB, 1.0, C, lda, lower, S, s);
+  };
+  // first pair: panel A0, its update of B0, panel B0 -- nothing to overlap with yet
+  const int64_t a1 = P < n_pad ? P : n_pad, b1 = 2 * P < n_pad ? 2 * P : n_pad;
+  if ((rc = factor_panel<double>(A, lda, 0, R, 0, a1, logdet, info, 1, stream))) return rc;
+  if (b1 > a1) {
+    if ((rc = oz_slice_panel(A + a1 * lda, lda, R - a1, a1, wsY, R, S, stream))) return rc;
+    if ((rc = upd(wsY, a1, 0, 0, R - a1, b1 - a1, A + a1 * lda + a1, 1, stream))) return rc;
+    if ((rc = factor_panel<double>(A, lda, 0, R, a1, b1, logdet, info, 1, stream))) return rc;
+  }
+  for (int64_t kb = 0; kb + 2 * P < n_pad; kb += 2 * P) {
+    const int64_t ke = kb + 2 * P;                                   // pair [kb, ke) is factorised
+    const int64_t ke1 = ke + P < n_pad ? ke + P : n_pad;              // A' = [ke, ke1)
+    const int64_t ke2 = ke + 2 * P < n_pad ? ke + 2 * P : n_pad;      // B' = [ke1, ke2) (may be empty)
+    const int64_t W1 = ke1 - ke, W2 = ke2 - ke1, K2 = 2 * P;
+    if ((rc = oz_slice_panel(A + ke * lda + kb, lda, R - ke, K2, wsX, R, S, stream))) return rc;
+    if ((rc = ce(cudaEventRecord(la.fork, stream)))) return rc;
+    if ((rc = ce(cudaStreamWaitEvent(la.side, la.fork, 0)))) return rc;
+    if ((rc = ce(cudaStreamWaitEvent(la.bulk, la.fork, 0)))) return rc;
+    // block column A': its diagonal block on the chain stream (the leaf chain starts on it at once), the rows below on bulk
+    if ((rc = upd(wsX, K2, 0, 0, W1, W1, A + ke * lda + ke, 1, la.side))) return rc;
+    if ((rc = upd(wsX, K2, W1, 0, R - ke1, W1, A + ke1 * lda + ke, 0, la.bulk))) return rc;
+    // block column B' (rows from ke1 on): pair update now, on bulk -- ordered before the A' update of the same block below
+    if ((rc = upd(wsX, K2, W1, W1, R - ke1, W2, A + ke1 * lda + ke1, 1, la.bulk))) return rc;
+    if ((rc = factor_panel_split<double>(A, lda, 0, R, ke, ke1, logdet, info, 1, la.side, la))) return rc;  // ends joined with bulk
+    if (W2 > 0) {
+      if ((rc = oz_slice_panel(A + ke1 * lda + ke, lda, R - ke1, W1, wsY, R, S, la.side))) return rc;
+      if ((rc = upd(wsY, W1, 0, 0, W2, W2, A + ke1 * lda + ke1, 1, la.side))) return rc;
+      if ((rc = ce(cudaEventRecord(la.crit, la.side)))) return rc;  // Y is ready (and every earlier update of B' is done)
+      if ((rc = ce(cudaStreamWaitEvent(la.bulk, la.crit, 0)))) return rc;
+      if ((rc = upd(wsY, W1, W2, 0, R - ke2, W2, A + ke2 * lda + ke1, 0, la.bulk))) return rc;
+      if ((rc = factor_panel_split<double>(A, lda, 0, R, ke1, ke2, logdet, info, 1, la.side, la))) return rc;
+    }
+    if ((rc = ce(cudaEventRecord(la.join, la.side)))) return rc;
+    // the far part: everything right of the next pair, K = 1024, on the caller's stream
+    if ((rc = upd(wsX, K2, ke2 - ke, ke2 - ke, R - ke2, n_pad - ke2, A + ke2 * lda + ke2, 1, stream))) return rc;
+    if ((rc = ce(cudaStreamWaitEvent(stream, la.join, 0)))) return rc;
+  }
+  return 0;
+}
+
 template <typename T>
 static int potrf_driver(T* A, int64_t lda, int64_t a_bs, int64_t n_pad, int64_t extra_rows, T* logdet, int32_t* info,
                         int32_t batch, cudaStream_t stream, Trailing tr = Trailing()) {
@@ -916,6 +983,11 @@ static int potrf_driver(T* A, int64_t lda, int64_t a_bs, int64_t n_pad, int64_t 
   } suspend(emulation());
   int rc;
   Lookahead& la = lookahead();
+  if (tr.mode == MODE_OZAKI && sizeof(T) == 8 && batch == 1 && la.ok && NB_OUTER == 512 && n_pad >= 4096 &&
+      tr.ws_bytes >= potrf_pairs_ws_bytes(R, tr.slices) && getenv("GPK_NO_LOOKAHEAD") == nullptr &&
+      getenv("GPK_NO_PAIRS") == nullptr)
+    return potrf_driver_pairs(reinterpret_cast<double*>(A), lda, n_pad, extra_rows, reinterpret_cast<double*>(logdet), info,
+                              stream, tr.ws, tr.slices, la);
   const bool use_la = la.ok && n_pad > 2 * NB_OUTER && getenv("GPK_NO_LOOKAHEAD") == nullptr;
   const bool split = use_la && getenv("GPK_NO_SPLIT") == nullptr;
   auto ce = [](cudaError_t e) { return e == cudaSuccess ? 0 : -1000 - (int)e; };
@@ -1051,7 +1123,9 @@ int gpk_debug_leaf_phase_clock(void* buf16_int64) {
   return e == cudaSuccess ? 0 : -1000 - (int)e;
 }
 int64_t gpk_potrf_oz_ws_bytes(int64_t n_pad, int64_t extra_rows, int32_t slices) {
-  return gpk::oz_ws_bytes(n_pad + extra_rows, gpk::nb_outer(), slices);
+  const int64_t one = gpk::oz_ws_bytes(n_pad + extra_rows, gpk::nb_outer(), slices);
+  const int64_t pairs = gpk::potrf_pairs_ws_bytes(n_pad + extra_rows, slices);  // the pair scheme (n_pad >= 4096)
+  return n_pad >= 4096 && pairs > one ? pairs : one;
 }
 int gpk_potrf_f64(double* A, int64_t lda, int64_t a_bstride, int64_t n_pad, int64_t extra_rows, double* logdet,
                   int32_t* info, int32_t batch, void* stream) {

@@ -213,3 +213,23 @@ def test_auto_picks_slices_by_conditioning(S):
     assert out["auto"][0] == out["int8x8"][0]  # noise-free: 8 slices
     assert out["auto"][1] == out["int8x7"][1]  # known noise: 7 slices
     assert out["int8x7"][1] != out["int8x8"][1]
+
+
+@pytest.mark.parametrize("n", [4096, 4700, 5250, 6400])
+def test_pair_scheme_vs_native(S, n):
+    """n_pad >= 4096: the emulated factorisation updates the far trailing matrix once per PAIR of 512-panels with K = 1024
+    (``potrf_driver_pairs``).  Ragged tails (a last pair with a short or missing second panel) against the native fp64 path."""
+    rng = np.random.default_rng(n)
+    x = torch.as_tensor(rng.uniform(0, 4, (n, 3)), device="cuda")
+    y = torch.as_tensor(rng.standard_normal((n, 2)), device="cuda")  # two right-hand sides ride along as extra rows
+    f = S.GP(S.EQ().stretch(0.7) + 0.5 * S.Matern32())
+    out = {}
+    before = S.B.precision
+    try:
+        for prec in ("fp64", "int8x8", "auto"):
+            S.B.precision = prec
+            out[prec] = f(x, 0.05).logpdf(y).cpu().numpy()
+    finally:
+        S.B.precision = before
+    assert np.max(np.abs(out["int8x8"] - out["fp64"]) / np.abs(out["fp64"])) < 1e-12
+    assert np.max(np.abs(out["auto"] - out["fp64"]) / np.abs(out["fp64"])) < 1e-11
