@@ -425,8 +425,10 @@ def gpu_arm(args, rank, world, local_rank):
         del os.environ["GPK_NO_LOOKAHEAD"]
         slices = ops._oz_slices(True)  # the benchmarked factorisation: noise 0.1 of the variance -> well conditioned by construction
         mp = measured_peaks()
-        timing_note = ("CUDA events around every launch of the kernel on its own stream, inside whole logpdf steps, look-ahead "
-                       "streams off for these steps so launches do not share SMs (the timed region of `value` runs WITH look-ahead)")
+        timing_note = ("CUDA events around every launch of the kernel, inside whole logpdf steps run with GPK_NO_LOOKAHEAD=1: the same "
+                       "launches in the same order (pairs of 512-panels, far updates with K = 1024) on ONE stream, so that launches do "
+                       "not share SMs and the bracketed durations are per-kernel figures (the timed region of `value` overlaps them "
+                       "with the panel factorisations on side streams)")
         if o_launches > 0:
             # int8-slice emulation kernel: the work it does is S (S + 1) / 2 int8 GEMMs per fp64-equivalent GEMM
             n_prod = slices * (slices + 1) // 2
@@ -444,8 +446,9 @@ def gpu_arm(args, rank, world, local_rank):
                 "frac": achieved / peak, "traffic": (cap or {}).get("dram_bytes"),
                 "traffic_source": (cap or {}).get("source", "no committed capture of this kernel (profiles/r02_kernel_summaries.json)"),
                 "traffic_algorithmic_bytes": (cap or {}).get("algorithmic_bytes"),
-                "kernel": f"gpk::oz_gemm_kernel<{slices}> (UTCIMMA = tcgen05.mma.kind::i8; the K=512 trailing SYRK updates of "
-                          f"the Cholesky as {n_prod} exact int8 slice products per fp64 product)",
+                "kernel": f"gpk::oz_gemm_kernel<{slices}> (UTCIMMA = tcgen05.mma.kind::i8; the trailing SYRK updates of the Cholesky "
+                          f"-- K = 1024 per pair of panels for the far part, K = 512 inside a pair -- as {n_prod} exact int8 slice "
+                          f"products per fp64 product)",
                 "peak_source": peak_src,
                 "peak_sustained": (2.0 * float(mp["bf16_tflops_sustained"])) if mp and "bf16_tflops_sustained" in mp else None,
                 "frac_vs_sustained": (achieved / (2.0 * float(mp["bf16_tflops_sustained"]))) if mp and "bf16_tflops_sustained" in mp else None,

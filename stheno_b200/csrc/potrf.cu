@@ -908,6 +908,14 @@ static int potrf_driver_pairs(double* A, int64_t lda, int64_t n_pad, int64_t ext
                               cudaStream_t stream, void* ws, int32_t S, Lookahead& la) {
   auto ce = [](cudaError_t e) { return e == cudaSuccess ? 0 : -1000 - (int)e; };
   const int64_t R = n_pad + extra_rows, P = 512;
+  // GPK_NO_LOOKAHEAD (bench.py's in-situ kernel timing): the same schedule on ONE stream, so that event-bracketed launch
+  // durations are per-kernel figures
+  const bool nola = getenv("GPK_NO_LOOKAHEAD") != nullptr;
+  const cudaStream_t side = nola ? stream : la.side, bulk = nola ? stream : la.bulk;
+  auto factor = [&](int64_t c0, int64_t c1) -> int {
+    if (nola) return factor_panel<double>(A, lda, 0, R, c0, c1, logdet, info, 1, stream);
+    return factor_panel_split<double>(A, lda, 0, R, c0, c1, logdet, info, 1, side, la);  // ends joined with bulk
+  };
   void* wsX = ws;                                                                       // [S][R][1024] + scales
   void* wsY = static_cast<char*>(ws) + ((oz_ws_bytes(R, 2 * P, S) + 1023) & ~int64_t(1023));  // [S][R][512] + scales
   int rc;
@@ -931,23 +939,23 @@ static int potrf_driver_pairs(double* A, int64_t lda, int64_t n_pad, int64_t ext
     const int64_t W1 = ke1 - ke, W2 = ke2 - ke1, K2 = 2 * P;
     if ((rc = oz_slice_panel(A + ke * lda + kb, lda, R - ke, K2, wsX, R, S, stream))) return rc;
     if ((rc = ce(cudaEventRecord(la.fork, stream)))) return rc;
-    if ((rc = ce(cudaStreamWaitEvent(la.side, la.fork, 0)))) return rc;
-    if ((rc = ce(cudaStreamWaitEvent(la.bulk, la.fork, 0)))) return rc;
+    if ((rc = ce(cudaStreamWaitEvent(side, la.fork, 0)))) return rc;
+    if ((rc = ce(cudaStreamWaitEvent(bulk, la.fork, 0)))) return rc;
     // block column A': its diagonal block on the chain stream (the leaf chain starts on it at once), the rows below on bulk
-    if ((rc = upd(wsX, K2, 0, 0, W1, W1, A + ke * lda + ke, 1, la.side))) return rc;
-    if ((rc = upd(wsX, K2, W1, 0, R - ke1, W1, A + ke1 * lda + ke, 0, la.bulk))) return rc;
+    if ((rc = upd(wsX, K2, 0, 0, W1, W1, A + ke * lda + ke, 1, side))) return rc;
+    if ((rc = upd(wsX, K2, W1, 0, R - ke1, W1, A + ke1 * lda + ke, 0, bulk))) return rc;
     // block column B' (rows from ke1 on): pair update now, on bulk -- ordered before the A' update of the same block below
-    if ((rc = upd(wsX, K2, W1, W1, R - ke1, W2, A + ke1 * lda + ke1, 1, la.bulk))) return rc;
-    if ((rc = factor_panel_split<double>(A, lda, 0, R, ke, ke1, logdet, info, 1, la.side, la))) return rc;  // ends joined with bulk
+    if ((rc = upd(wsX, K2, W1, W1, R - ke1, W2, A + ke1 * lda + ke1, 1, bulk))) return rc;
+    if ((rc = factor(ke, ke1))) return rc;
     if (W2 > 0) {
-      if ((rc = oz_slice_panel(A + ke1 * lda + ke, lda, R - ke1, W1, wsY, R, S, la.side))) return rc;
-      if ((rc = upd(wsY, W1, 0, 0, W2, W2, A + ke1 * lda + ke1, 1, la.side))) return rc;
-      if ((rc = ce(cudaEventRecord(la.crit, la.side)))) return rc;  // Y is ready (and every earlier update of B' is done)
-      if ((rc = ce(cudaStreamWaitEvent(la.bulk, la.crit, 0)))) return rc;
-      if ((rc = upd(wsY, W1, W2, 0, R - ke2, W2, A + ke2 * lda + ke1, 0, la.bulk))) return rc;
-      if ((rc = factor_panel_split<double>(A, lda, 0, R, ke1, ke2, logdet, info, 1, la.side, la))) return rc;
+      if ((rc = oz_slice_panel(A + ke1 * lda + ke, lda, R - ke1, W1, wsY, R, S, side))) return rc;
+      if ((rc = upd(wsY, W1, 0, 0, W2, W2, A + ke1 * lda + ke1, 1, side))) return rc;
+      if ((rc = ce(cudaEventRecord(la.crit, side)))) return rc;  // Y is ready (and every earlier update of B' is done)
+      if ((rc = ce(cudaStreamWaitEvent(bulk, la.crit, 0)))) return rc;
+      if ((rc = upd(wsY, W1, W2, 0, R - ke2, W2, A + ke2 * lda + ke1, 0, bulk))) return rc;
+      if ((rc = factor(ke1, ke2))) return rc;
     }
-    if ((rc = ce(cudaEventRecord(la.join, la.side)))) return rc;
+    if ((rc = ce(cudaEventRecord(la.join, side)))) return rc;
     // the far part: everything right of the next pair, K = 1024, on the caller's stream
     if ((rc = upd(wsX, K2, ke2 - ke, ke2 - ke, R - ke2, n_pad - ke2, A + ke2 * lda + ke2, 1, stream))) return rc;
     if ((rc = ce(cudaStreamWaitEvent(stream, la.join, 0)))) return rc;
@@ -984,8 +992,7 @@ static int potrf_driver(T* A, int64_t lda, int64_t a_bs, int64_t n_pad, int64_t 
   int rc;
   Lookahead& la = lookahead();
   if (tr.mode == MODE_OZAKI && sizeof(T) == 8 && batch == 1 && la.ok && NB_OUTER == 512 && n_pad >= 4096 &&
-      tr.ws_bytes >= potrf_pairs_ws_bytes(R, tr.slices) && getenv("GPK_NO_LOOKAHEAD") == nullptr &&
-      getenv("GPK_NO_PAIRS") == nullptr)
+      tr.ws_bytes >= potrf_pairs_ws_bytes(R, tr.slices) && getenv("GPK_NO_PAIRS") == nullptr)
     return potrf_driver_pairs(reinterpret_cast<double*>(A), lda, n_pad, extra_rows, reinterpret_cast<double*>(logdet), info,
                               stream, tr.ws, tr.slices, la);
   const bool use_la = la.ok && n_pad > 2 * NB_OUTER && getenv("GPK_NO_LOOKAHEAD") == nullptr;
