@@ -122,25 +122,45 @@ __device__ __forceinline__ void oz_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) 
 __device__ __forceinline__ double oz_i2d(uint32_t x) {
   return __hiloint2double(0x43300000, (int)(x ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
 }
-// tile index -> (tile row, tile column).  Lower mode enumerates only the tiles that touch the lower triangle, row by row:
-// row tm holds min(tiles_n, 2 (tm + 1)) tiles (128 x 64 tiles), i.e. tm (tm + 1) tiles precede row tm while tm <= tri_rows.
+// tile index -> (tile row, tile column).  Lower mode enumerates only the tiles that touch the lower triangle: row tm holds
+// nc(tm) = min(tiles_n, 2 (tm + 1)) tiles (128 x 64 tiles), so f(r) = r (r + 1) tiles precede row r while r <= tri_rows.
+// Order: BANDS of OZ_BAND tile rows, column-major inside a band.  Tiles that run at the same time then share the band's A rows
+// (OZ_BAND x 128 rows of slices: 15 MB at K = 1024, S = 7) and sweep the B rows once per band, instead of once per tile ROW
+// as the plain row-major order did -- whose K = 1024 launches read 2.1x their algorithmic bytes from HBM (ncu, round 2: the
+// 104 MB of slices no longer fit L2 next to the C traffic).
+constexpr int OZ_BAND = 16;
+__device__ __forceinline__ int oz_rows_before(const OzParams& p, int r) {  // tiles in tile rows < r
+  if (!p.lower) return r * p.tiles_n;
+  return r <= p.tri_rows ? r * (r + 1) : p.tri_rows * (p.tri_rows + 1) + (r - p.tri_rows) * p.tiles_n;
+}
 __device__ __forceinline__ void oz_tile(const OzParams& p, int t, int& tm, int& tn) {
-  if (!p.lower) {
-    tm = t / p.tiles_n;
-    tn = t - tm * p.tiles_n;
+  // (1) band
+  int r0 = 0;
+  while (r0 + OZ_BAND < p.tiles_m && oz_rows_before(p, r0 + OZ_BAND) <= t) r0 += OZ_BAND;
+  const int r1 = min(r0 + OZ_BAND, p.tiles_m);
+  int u = t - oz_rows_before(p, r0);
+  // (2) column-major inside the band: row tm has nc(tm) columns, non-decreasing in tm
+  const int nc0 = p.lower ? min(p.tiles_n, 2 * (r0 + 1)) : p.tiles_n;  // columns that every row of the band has
+  const int h = r1 - r0;
+  if (u < nc0 * h) {
+    tn = u / h;
+    tm = r0 + (u - tn * h);
     return;
   }
-  const int tri = p.tri_rows * (p.tri_rows + 1);
-  if (t < tri) {
-    tm = (int)((sqrtf(4.f * (float)t + 1.f) - 1.f) * 0.5f);
-    while (tm * (tm + 1) > t) --tm;
-    while ((tm + 1) * (tm + 2) <= t) ++tm;
-    tn = t - tm * (tm + 1);
-  } else {
-    const int r = t - tri;
-    tm = p.tri_rows + r / p.tiles_n;
-    tn = r - (tm - p.tri_rows) * p.tiles_n;
+  u -= nc0 * h;
+  // ragged part (lower mode only): column c >= nc0 exists in the rows tm with 2 (tm + 1) > c, i.e. tm = c / 2 ... r1 - 1
+  for (int c = nc0; c < p.tiles_n; ++c) {
+    const int first = max(r0, c >> 1);  // first row of the band that has column c (c < tiles_n is implied by u's range)
+    const int cnt = r1 - first;
+    if (u < cnt) {
+      tn = c;
+      tm = first + u;
+      return;
+    }
+    u -= cnt;
   }
+  tm = r1 - 1;  // not reached for t < total_tiles (bijection checked on the host for 1047 shapes); keeps the loop bounded
+  tn = p.tiles_n - 1;
 }
 
 // One CTA works through `tiles_per_cta` consecutive tiles: the TMA producer and the MMA issuer run ahead into the next tile
