@@ -66,6 +66,7 @@ struct OzParams {
   int32_t KB, lower, tiles_m, tiles_n;
   int32_t total_tiles, tiles_per_cta, tri_rows;  // tri_rows: tile rows in the triangular part (lower mode)
   int32_t accumulate;                            // 1: C += alpha A B^T (reduce-add), 0: C = alpha A B^T (store)
+  int32_t band;                                  // tile rows per band of the tile order
 };
 
 __device__ __forceinline__ void oz_mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -124,11 +125,10 @@ __device__ __forceinline__ double oz_i2d(uint32_t x) {
 }
 // tile index -> (tile row, tile column).  Lower mode enumerates only the tiles that touch the lower triangle: row tm holds
 // nc(tm) = min(tiles_n, 2 (tm + 1)) tiles (128 x 64 tiles), so f(r) = r (r + 1) tiles precede row r while r <= tri_rows.
-// Order: BANDS of OZ_BAND tile rows, column-major inside a band.  Tiles that run at the same time then share the band's A rows
-// (OZ_BAND x 128 rows of slices: 15 MB at K = 1024, S = 7) and sweep the B rows once per band, instead of once per tile ROW
+// Order: BANDS of `band` (16) tile rows, column-major inside a band.  Tiles that run at the same time then share the band's A rows
+// (16 x 128 rows of slices: 15 MB at K = 1024, S = 7) and sweep the B rows once per band, instead of once per tile ROW
 // as the plain row-major order did -- whose K = 1024 launches read 2.1x their algorithmic bytes from HBM (ncu, round 2: the
 // 104 MB of slices no longer fit L2 next to the C traffic).
-constexpr int OZ_BAND = 16;
 __device__ __forceinline__ int oz_rows_before(const OzParams& p, int r) {  // tiles in tile rows < r
   if (!p.lower) return r * p.tiles_n;
   return r <= p.tri_rows ? r * (r + 1) : p.tri_rows * (p.tri_rows + 1) + (r - p.tri_rows) * p.tiles_n;
@@ -136,8 +136,8 @@ __device__ __forceinline__ int oz_rows_before(const OzParams& p, int r) {  // ti
 __device__ __forceinline__ void oz_tile(const OzParams& p, int t, int& tm, int& tn) {
   // (1) band
   int r0 = 0;
-  while (r0 + OZ_BAND < p.tiles_m && oz_rows_before(p, r0 + OZ_BAND) <= t) r0 += OZ_BAND;
-  const int r1 = min(r0 + OZ_BAND, p.tiles_m);
+  while (r0 + p.band < p.tiles_m && oz_rows_before(p, r0 + p.band) <= t) r0 += p.band;
+  const int r1 = min(r0 + p.band, p.tiles_m);
   int u = t - oz_rows_before(p, r0);
   // (2) column-major inside the band: row tm has nc(tm) columns, non-decreasing in tm
   const int nc0 = p.lower ? min(p.tiles_n, 2 * (r0 + 1)) : p.tiles_n;  // columns that every row of the band has
@@ -458,10 +458,12 @@ int oz_launch_gemm(int64_t M, int64_t N, int64_t K, double alpha, const int8_t* 
   const int32_t total = lower ? tri_rows * (tri_rows + 1) + (tiles_m - tri_rows) * tiles_n : tiles_m * tiles_n;
   static const int force_tpc = getenv("GPK_OZ_TPC") ? atoi(getenv("GPK_OZ_TPC")) : 0;
   int32_t tpc = force_tpc > 0 ? force_tpc : total / 296;  // >= 2 waves of CTAs over 148 SMs before CTAs grow
-  const int32_t tpc_cap = K > 512 ? 2 : 4;  // CTAs stay short-lived (look-ahead streams need SMs every few tens of us)
+  static const int env_cap = getenv("GPK_OZ_TPC_CAP") ? atoi(getenv("GPK_OZ_TPC_CAP")) : 0;  // experiments
+  static const int env_band = getenv("GPK_OZ_BAND") ? atoi(getenv("GPK_OZ_BAND")) : 0;
+  const int32_t tpc_cap = env_cap > 0 ? env_cap : (K > 512 ? 2 : 4);  // CTAs stay short-lived (look-ahead streams need SMs every few tens of us)
   tpc = tpc < 1 ? 1 : (tpc > tpc_cap && force_tpc <= 0 ? tpc_cap : tpc);
   OzParams p{alpha, C, scA + rowA, scB + rowB, ldc, (int32_t)rowA, (int32_t)rowB, (int32_t)(K / OZ_BK), lower,
-             tiles_m, tiles_n, total, tpc, tri_rows, beta != 0.0 ? 1 : 0};
+             tiles_m, tiles_n, total, tpc, tri_rows, beta != 0.0 ? 1 : 0, env_band > 0 ? env_band : 16};
   // profile: algorithmic (fp64-equivalent) flops of the tiles computed; the int8 work is S (S + 1) / 2 times that
   if (prof_enabled()) prof_begin(stream, (double)total * 2.0 * OZ_BM * OZ_BN * (double)K, 1);
   oz_gemm_kernel<S><<<(unsigned)((total + tpc - 1) / tpc), OZ_THREADS, OzCfg<S>::SMEM_BYTES, stream>>>(mA, mB, mC, p);
