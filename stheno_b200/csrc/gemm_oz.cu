@@ -460,10 +460,14 @@ int oz_launch_gemm(int64_t M, int64_t N, int64_t K, double alpha, const int8_t* 
   int32_t tpc = force_tpc > 0 ? force_tpc : total / 296;  // >= 2 waves of CTAs over 148 SMs before CTAs grow
   static const int env_cap = getenv("GPK_OZ_TPC_CAP") ? atoi(getenv("GPK_OZ_TPC_CAP")) : 0;  // experiments
   static const int env_band = getenv("GPK_OZ_BAND") ? atoi(getenv("GPK_OZ_BAND")) : 0;
+  // band height of the tile order: as many tile rows as keep the band's A slices (128 K S bytes per tile row) within ~24 MB
+  // of L2, at most 16 (K = 1024, S = 7: 16 rows = 15 MB; the K = 8192 products of the triangular solves: 2-3 rows)
+  int32_t band = (int32_t)((24ll << 20) / (128ll * K * S));
+  band = env_band > 0 ? env_band : (band < 1 ? 1 : (band > 16 ? 16 : band));
   const int32_t tpc_cap = env_cap > 0 ? env_cap : (K > 512 ? 2 : 4);  // CTAs stay short-lived (look-ahead streams need SMs every few tens of us)
   tpc = tpc < 1 ? 1 : (tpc > tpc_cap && force_tpc <= 0 ? tpc_cap : tpc);
   OzParams p{alpha, C, scA + rowA, scB + rowB, ldc, (int32_t)rowA, (int32_t)rowB, (int32_t)(K / OZ_BK), lower,
-             tiles_m, tiles_n, total, tpc, tri_rows, beta != 0.0 ? 1 : 0, env_band > 0 ? env_band : 16};
+             tiles_m, tiles_n, total, tpc, tri_rows, beta != 0.0 ? 1 : 0, band};
   // profile: algorithmic (fp64-equivalent) flops of the tiles computed; the int8 work is S (S + 1) / 2 times that
   if (prof_enabled()) prof_begin(stream, (double)total * 2.0 * OZ_BM * OZ_BN * (double)K, 1);
   oz_gemm_kernel<S><<<(unsigned)((total + tpc - 1) / tpc), OZ_THREADS, OzCfg<S>::SMEM_BYTES, stream>>>(mA, mB, mC, p);
