@@ -541,3 +541,32 @@ def test_rq_kernel(S):
     approx(f(x, 0.1).logpdf(y), O.fdd_logpdf(spec, x, 0.1, y), rtol=1e-10, atol=0)
     approx((f | (f(x, 0.1), y))(xs).mean, O.posterior(spec, x, 0.1, y, xs)[0], rtol=1e-8, atol=1e-9)
     assert str(S.RQ(0.5)) == "RQ(0.5)"
+
+
+def test_block_joint_with_unequal_blocks_and_mixed_noise(S):
+    # B.block assembly kept symbolic (matrix.BlockDense): unequal block sizes, scalar / vector / no noise per block, a
+    # non-symbolic (conditioned) block next to symbolic ones -- logpdf, dense matrix and a sample against the oracle
+    rng = np.random.default_rng(91)
+    x1, x2, x3 = rng.standard_normal((37, 2)), rng.standard_normal((140, 2)), rng.standard_normal((5, 2))
+    m = S.Measure()
+    f = S.GP(S.EQ().stretch(1.2), measure=m)
+    g = S.GP(0.7 * S.Matern52(), measure=m)
+    h = f + 2.0 * g
+    nv = rng.uniform(0.1, 0.3, 140)
+    fdds = (f(x1, 0.2), h(x2, nv), g(x3))
+    y = [rng.standard_normal(37), rng.standard_normal(140), rng.standard_normal(5)]
+    kf, kg = ("stretched", 1.2, ("eq",)), ("scaled", 0.7, ("matern52",))
+    kh = ("sum", kf, ("scaled", 4.0, kg))
+    khg = ("scaled", 2.0, kg)
+    zero = ("zero",)
+    specs = [[kf, kf, zero], [kf, kh, khg], [zero, khg, kg]]
+    K = O.mo_block_kernel(specs, [x1, x2, x3])
+    K[:37, :37] += 0.2 * np.eye(37)
+    K[37:177, 37:177] += np.diag(nv)
+    want = float(O.normal_logpdf(None, K, np.concatenate(y)))
+    got = m.logpdf(*[(fd, yi) for fd, yi in zip(fdds, y)])
+    approx(got, want, rtol=1e-10, atol=0)
+    from stheno_b200.model.observations import combine
+
+    joint = combine(*fdds)
+    approx(S.B.dense(joint.var), K, rtol=1e-10, atol=1e-12)
