@@ -264,6 +264,11 @@ void gpk_gemm_profile_enable(int32_t on);
 int gpk_gemm_profile_read_kind(int32_t kind, double* total_ms, double* total_flops, int64_t* launches); /* 0 DMMA, 1 int8 emulation, -1 all */
 int gpk_gemm_profile_read(double* total_ms_host, double* total_flops_host, int64_t* launches_host);
 
+/* Test helper (no GPU needed): the tile order of the emulated GEMM evaluated on the host -- tile index t of a launch with
+ * tiles_m x tiles_n tiles (128 x 64; `lower`: only the tiles touching the lower triangle; `band`: tile rows per band) ->
+ * (*tm, *tn).  Returns the number of tiles of the launch. */
+int32_t gpk_debug_oz_tile(int32_t lower, int32_t tiles_m, int32_t tiles_n, int32_t band, int32_t t, int32_t* tm, int32_t* tn);
+
 /* Measurement helper (tools/time_leaf_phases.py): while `buf` (>= 16 int64, device memory) is set, every leaf-Cholesky launch
  * records clock64() at its phase boundaries there; NULL switches it off.  Synchronises the device. */
 int gpk_debug_leaf_phase_clock(void* buf16_int64);

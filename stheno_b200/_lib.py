@@ -61,6 +61,7 @@ _PLAIN = {
     "gpk_sparse_ws_elems": ([_i64, _i64], _i64),
     "gpk_probe_dmma_tflops": ([], c_double),
     "gpk_debug_leaf_phase_clock": ([_ptr], c_int32),
+    "gpk_debug_oz_tile": ([_i32, _i32, _i32, _i32, _i32, POINTER(c_int32), POINTER(c_int32)], c_int32),
     "gpk_launch_count": ([], _i64),
     "gpk_launch_count_reset": ([], None),
     "gpk_potrf_f64_tf32x3": ([_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _i32, _ptr, _i64, _ptr], c_int32),

@@ -129,18 +129,18 @@ __device__ __forceinline__ double oz_i2d(uint32_t x) {
 // (16 x 128 rows of slices: 15 MB at K = 1024, S = 7) and sweep the B rows once per band, instead of once per tile ROW
 // as the plain row-major order did -- whose K = 1024 launches read 2.1x their algorithmic bytes from HBM (ncu, round 2: the
 // 104 MB of slices no longer fit L2 next to the C traffic).
-__device__ __forceinline__ int oz_rows_before(const OzParams& p, int r) {  // tiles in tile rows < r
+__host__ __device__ __forceinline__ int oz_rows_before(const OzParams& p, int r) {  // tiles in tile rows < r
   if (!p.lower) return r * p.tiles_n;
   return r <= p.tri_rows ? r * (r + 1) : p.tri_rows * (p.tri_rows + 1) + (r - p.tri_rows) * p.tiles_n;
 }
-__device__ __forceinline__ void oz_tile(const OzParams& p, int t, int& tm, int& tn) {
+__host__ __device__ __forceinline__ void oz_tile(const OzParams& p, int t, int& tm, int& tn) {
   // (1) band
   int r0 = 0;
   while (r0 + p.band < p.tiles_m && oz_rows_before(p, r0 + p.band) <= t) r0 += p.band;
-  const int r1 = min(r0 + p.band, p.tiles_m);
+  const int r1 = (r0 + p.band < p.tiles_m) ? r0 + p.band : p.tiles_m;
   int u = t - oz_rows_before(p, r0);
   // (2) column-major inside the band: row tm has nc(tm) columns, non-decreasing in tm
-  const int nc0 = p.lower ? min(p.tiles_n, 2 * (r0 + 1)) : p.tiles_n;  // columns that every row of the band has
+  const int nc0 = (p.lower && 2 * (r0 + 1) < p.tiles_n) ? 2 * (r0 + 1) : p.tiles_n;  // columns that every row of the band has
   const int h = r1 - r0;
   if (u < nc0 * h) {
     tn = u / h;
@@ -150,7 +150,7 @@ __device__ __forceinline__ void oz_tile(const OzParams& p, int t, int& tm, int& 
   u -= nc0 * h;
   // ragged part (lower mode only): column c >= nc0 exists in the rows tm with 2 (tm + 1) > c, i.e. tm = c / 2 ... r1 - 1
   for (int c = nc0; c < p.tiles_n; ++c) {
-    const int first = max(r0, c >> 1);  // first row of the band that has column c (c < tiles_n is implied by u's range)
+    const int first = (c >> 1) > r0 ? (c >> 1) : r0;  // first row of the band that has column c (c < tiles_n is implied by u's range)
     const int cnt = r1 - first;
     if (u < cnt) {
       tn = c;
@@ -590,6 +590,27 @@ int64_t gpk_f64_emulation_scratch_bytes(int64_t M, int64_t N, int64_t K, int32_t
 }
 
 int64_t gpk_oz_ws_bytes(int64_t rows, int64_t K, int32_t slices) { return gpk::oz_ws_bytes(rows, K, slices); }
+
+// Host-side evaluation of the emulation GEMM's tile order (the SAME function the kernel runs): tile index t of a launch with
+// tiles_m x tiles_n tiles of 128 x 64 -> (tile row, tile column).  Returns the number of tiles of the launch.  Lets the
+// CPU test-suite prove that the order is a bijection for every shape without a GPU (an unbounded / wrong order would hang
+// or corrupt a launch on the device).
+int32_t gpk_debug_oz_tile(int32_t lower, int32_t tiles_m, int32_t tiles_n, int32_t band, int32_t t, int32_t* tm, int32_t* tn) {
+  gpk::OzParams p{};
+  p.lower = lower;
+  p.tiles_m = tiles_m;
+  p.tiles_n = tiles_n;
+  p.band = band;
+  p.tri_rows = lower ? (tiles_m < tiles_n / 2 ? tiles_m : tiles_n / 2) : 0;
+  p.total_tiles = lower ? p.tri_rows * (p.tri_rows + 1) + (tiles_m - p.tri_rows) * tiles_n : tiles_m * tiles_n;
+  if (t >= 0 && t < p.total_tiles && tm && tn) {
+    int a = 0, b = 0;
+    gpk::oz_tile(p, t, a, b);
+    *tm = a;
+    *tn = b;
+  }
+  return p.total_tiles;
+}
 
 int gpk_gemm_nt_f64_oz(int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, const double* B,
                        int64_t ldb, double beta, double* C, int64_t ldc, int32_t lower, int32_t slices, void* ws,

@@ -62,3 +62,33 @@ def test_flat_kernel_descriptor():
     assert isinstance(0 * S.EQ(), S.ZeroKernel) and (S.EQ() + S.ZeroKernel()).render() == "EQ()"
     assert (S.EQ() * (S.EQ() + S.Matern12())).flat_terms() is not None
     assert len(((S.EQ() + S.Matern12()) * (S.EQ() + S.Linear())).flat_terms()) == 4
+
+
+def test_emulated_gemm_tile_order_is_a_bijection():
+    """The banded, column-major tile order of the emulation GEMM (``oz_tile`` in csrc/gemm_oz.cu), evaluated on the HOST
+    through ``gpk_debug_oz_tile`` -- the very function the kernel runs: every tile of a launch exactly once, inside the
+    lower triangle in lower mode, for square / tall / ragged shapes and band heights 1..16 (no GPU needed; a wrong order
+    would corrupt or hang a launch on the device)."""
+    import ctypes
+
+    from stheno_b200 import _lib
+
+    lib = _lib.load()
+    tm, tn = ctypes.c_int32(), ctypes.c_int32()
+    shapes = [(1, 2), (2, 4), (3, 2), (5, 10), (16, 32), (17, 34), (33, 8), (40, 80), (64, 16), (114, 228), (120, 8)]
+    for lower in (0, 1):
+        for tiles_m, tiles_n in shapes:
+            if lower and tiles_n > 2 * tiles_m:
+                continue
+            for band in (1, 3, 16):
+                total = lib.gpk_debug_oz_tile(lower, tiles_m, tiles_n, band, -1, None, None)
+                tri = min(tiles_m, tiles_n // 2) if lower else 0
+                assert total == (tri * (tri + 1) + (tiles_m - tri) * tiles_n if lower else tiles_m * tiles_n)
+                seen = set()
+                for t in range(total):
+                    lib.gpk_debug_oz_tile(lower, tiles_m, tiles_n, band, t, ctypes.byref(tm), ctypes.byref(tn))
+                    a, b = tm.value, tn.value
+                    assert 0 <= a < tiles_m and 0 <= b < tiles_n, (lower, tiles_m, tiles_n, band, t, a, b)
+                    assert not lower or b < min(tiles_n, 2 * (a + 1)), (lower, tiles_m, tiles_n, band, t, a, b)
+                    seen.add((a, b))
+                assert len(seen) == total, (lower, tiles_m, tiles_n, band)
