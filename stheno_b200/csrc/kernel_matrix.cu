@@ -336,9 +336,11 @@ __device__ __forceinline__ float fast_factor<float, GPK_MATERN52>(float d2, int 
 }
 
 // (Round 2 also built a variant that walks a strip of 8 column tiles per CTA with the next y tile prefetched by the TMA engine
-//  into a second buffer: 0.507 ms instead of 0.585 ms at n = 16384 in isolation, but it dead-locked on one of the small ragged
-//  shapes of tests/test_gpu_primitives.py on the GPU box, and a hang costs the whole lease -- it was reverted; the one-tile
-//  kernel below passed the complete GPU suite.)
+//  into a second buffer: 0.507 ms instead of 0.585 ms at n = 16384 in isolation.  It hung the GPU test-suite and was reverted
+//  -- a hang costs the whole lease.  Cause, found afterwards: its "can the bulk-copy engine be used" test looked at the byte
+//  count of the LAST tile of the strip only, but with identity padding the ragged tile (the one that contains column n2) is
+//  followed by empty padding tiles, so a 24-byte cp.async.bulk (n2 = 3, d = 1) was issued and its mbarrier never completed.
+//  A strip version has to test every tile of its strip.)
 template <typename T, int KIND>
 __global__ void __launch_bounds__(KM_THREADS, 2) kernel_matrix_fast_kernel(const KmParams p) {
   const int tile_c = blockIdx.x, tile_r = blockIdx.y, b = blockIdx.z;
