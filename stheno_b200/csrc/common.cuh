@@ -50,7 +50,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(phase));
+      "r"(phase)
+      : "memory");  // the data the barrier guards must not be read before the wait
 }
 __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile(

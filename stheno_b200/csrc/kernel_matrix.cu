@@ -335,14 +335,9 @@ __device__ __forceinline__ float fast_factor<float, GPK_MATERN52>(float d2, int 
   return (1.0f + s + 1.6666666666666667f * d2) * expf(-s);
 }
 
-// (Round 2 also built a variant that walks a strip of 8 column tiles per CTA with the next y tile prefetched by the TMA engine
-//  into a second buffer: 0.507 ms instead of 0.585 ms at n = 16384 in isolation.  It hung the GPU test-suite and was reverted
-//  -- a hang costs the whole lease.  Cause, found afterwards: its "can the bulk-copy engine be used" test looked at the byte
-//  count of the LAST tile of the strip only, but with identity padding the ragged tile (the one that contains column n2) is
-//  followed by empty padding tiles, so a 24-byte cp.async.bulk (n2 = 3, d = 1) was issued and its mbarrier never completed.
-//  A strip version has to test every tile of its strip.)
+// ---- one tile per CTA (round-2 first version; GPK_K1_ONE_TILE=1 selects it for A/B comparisons) ----
 template <typename T, int KIND>
-__global__ void __launch_bounds__(KM_THREADS, 2) kernel_matrix_fast_kernel(const KmParams p) {
+__global__ void __launch_bounds__(KM_THREADS, 2) kernel_matrix_fast1_kernel(const KmParams p) {
   const int tile_c = blockIdx.x, tile_r = blockIdx.y, b = blockIdx.z;
   const bool lower = p.flags & GPK_KM_LOWER;
   if (lower && (tile_c >> 1) > (tile_r >> 1)) return;
@@ -441,6 +436,148 @@ __global__ void __launch_bounds__(KM_THREADS, 2) kernel_matrix_fast_kernel(const
   }
 }
 
+constexpr int KM_STRIP = 8;  // column tiles per CTA of the fast kernel
+
+// One CTA = one row tile x a strip of up to KM_STRIP column tiles.  The x rows are staged once; the y rows of tile c + 1 are
+// fetched by the TMA engine (double-buffered, one mbarrier per buffer) while tile c is evaluated, so the bulk-copy latency,
+// the transposition and the barriers of a tile hide under the arithmetic of its predecessor (round-2 ncu of the
+// one-tile-per-CTA version: FP64 pipe 35 % busy with 3 CTAs per SM -- the per-tile prologue was as long as the tile's math).
+template <typename T, int KIND>
+__global__ void __launch_bounds__(KM_THREADS, 3) kernel_matrix_fast_kernel(const KmParams p) {
+  const int tile_r = blockIdx.y, b = blockIdx.z;
+  const bool lower = p.flags & GPK_KM_LOWER;
+  const int tiles_x = (int)((p.cols_out + KM_TILE - 1) / KM_TILE);
+  const int c_begin = blockIdx.x * KM_STRIP;
+  int c_end = min(c_begin + KM_STRIP, tiles_x);
+  // LOWER: tiles strictly above the diagonal at 128-granularity are never written
+  if (lower) c_end = min(c_end, ((tile_r >> 1) + 1) * 2);
+  if (c_begin >= c_end) return;
+  const bool same_obj = p.flags & GPK_KM_SAME;
+  const int d = p.d;
+  const int g = p.desc.fac_group[0];
+  const int64_t r0 = (int64_t)tile_r * KM_TILE;
+
+  extern __shared__ __align__(16) unsigned char km_smem[];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ double tab[64];
+  T* xs = reinterpret_cast<T*>(km_smem);        // [64][d]
+  T* ysb = xs + (size_t)KM_TILE * d;             // [2][64][d]
+  T* yt = ysb + (size_t)2 * KM_TILE * d;         // [d][65]
+  const T* xg = static_cast<const T*>(p.xg) + (int64_t)b * p.x_bstride + g * p.xg_gstride + r0 * d;
+  const T* yg0 = static_cast<const T*>(p.yg) + (int64_t)b * p.y_bstride + g * p.yg_gstride;
+  if (sizeof(T) == 8 && threadIdx.x < 64) tab[threadIdx.x] = exp2((double)threadIdx.x * 0.015625);
+
+  const int xr = (int)max((int64_t)0, min((int64_t)KM_TILE, p.n - r0));
+  const uint32_t xbytes = (uint32_t)xr * d * sizeof(T);
+  // the bulk-copy engine needs 16-byte aligned addresses and sizes: every tile of the strip has to qualify
+  bool bulk = (xbytes % 16 == 0) && ((KM_TILE * d * sizeof(T)) % 16 == 0) && (reinterpret_cast<uintptr_t>(xg) % 16 == 0) &&
+              (reinterpret_cast<uintptr_t>(yg0) % 16 == 0);
+  // EVERY tile of the strip has to qualify (16-byte multiple): with identity padding the ragged tile -- the one that contains
+  // column n2 -- is followed by empty padding tiles, so looking at the strip's last tile only is not enough (that oversight
+  // issued a 24-byte cp.async.bulk whose mbarrier never completed: the hang of the first strip version)
+  for (int c = c_begin; c < c_end; ++c) {
+    const int yr_c = (int)max((int64_t)0, min((int64_t)KM_TILE, p.n2 - (int64_t)c * KM_TILE));
+    bulk = bulk && (((uint32_t)yr_c * d * sizeof(T)) % 16 == 0);
+  }
+  auto y_rows = [&](int c) { return (int)max((int64_t)0, min((int64_t)KM_TILE, p.n2 - (int64_t)c * KM_TILE)); };
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bars[0], 1);
+      mbar_init(&bars[1], 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // x rows + the first y tile arrive on buffer 0's barrier
+      const uint32_t yb = (uint32_t)y_rows(c_begin) * d * sizeof(T);
+      mbar_arrive_expect_tx(&bars[0], xbytes + yb);
+      if (xbytes) bulk_copy_g2s(xs, xg, xbytes, &bars[0]);
+      if (yb) bulk_copy_g2s(ysb, yg0 + (int64_t)c_begin * KM_TILE * d, yb, &bars[0]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < xr * d; i += KM_THREADS) xs[i] = xg[i];
+  }
+
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  T* out = static_cast<T*>(p.out) + (int64_t)b * p.o_bstride;
+  const T* nv = p.noise_vec ? static_cast<const T*>(p.noise_vec) + (int64_t)b * p.nv_bstride : nullptr;
+  const bool pad_id = p.flags & GPK_KM_PAD_IDENTITY;
+  const T coef = (T)p.desc.coef[0];
+  uint32_t phases = 0u;  // bit b = parity the next wait on bars[b] expects
+
+  for (int c = c_begin; c < c_end; ++c) {
+    const int buf = (c - c_begin) & 1;
+    const int64_t c0 = (int64_t)c * KM_TILE;
+    const int yr = y_rows(c);
+    T* ys = ysb + (size_t)buf * KM_TILE * d;
+    if (bulk) {
+      if (threadIdx.x == 0 && c + 1 < c_end) {  // prefetch the next y tile into the other buffer (freed one iteration ago)
+        const uint32_t yb = (uint32_t)y_rows(c + 1) * d * sizeof(T);
+        fence_proxy_async();  // the generic-proxy reads of that buffer (last tile's transposition) precede the async write
+        mbar_arrive_expect_tx(&bars[buf ^ 1], yb);
+        if (yb) bulk_copy_g2s(ysb + (size_t)(buf ^ 1) * KM_TILE * d, yg0 + (c0 + KM_TILE) * d, yb, &bars[buf ^ 1]);
+      }
+      mbar_wait(&bars[buf], (phases >> buf) & 1u);
+      phases ^= 1u << buf;
+    } else {
+      const T* yg = yg0 + c0 * d;
+      for (int i = threadIdx.x; i < yr * d; i += KM_THREADS) ys[i] = yg[i];
+      __syncthreads();
+    }
+    // transpose the y rows to [k][64 (+1 pad)]: the 16 column-threads of a half-warp then read consecutive words
+    for (int idx = threadIdx.x; idx < yr * d; idx += KM_THREADS) {
+      const int cc = idx / d, k = idx - cc * d;
+      yt[(size_t)k * (KM_TILE + 1) + cc] = ys[idx];
+    }
+    __syncthreads();
+
+    T d2[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d2[i][j] = T(0);
+    const T* xr_ = xs + (size_t)(ty * 4) * d;
+    const T* yc_ = yt + tx;
+#pragma unroll 2
+    for (int k = 0; k < d; ++k) {
+      T xv[4], yv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xv[i] = xr_[i * d + k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) yv[j] = yc_[(size_t)k * (KM_TILE + 1) + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const T df = xv[i] - yv[j];
+          d2[i][j] = fma(df, df, d2[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t r = r0 + ty * 4 + i;
+      if (r >= p.rows_out) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t cc = c0 + tx + 16 * j;
+        if (cc >= p.cols_out) continue;
+        T val;
+        if (r >= p.n || cc >= p.n2) {
+          val = (pad_id && r == cc) ? T(1) : T(0);
+        } else {
+          val = coef * fast_factor<T, KIND>(d2[i][j], d, tab);
+          if (same_obj && r == cc) {
+            val += (T)p.noise_scalar;
+            if (nv) val += nv[r];
+            val += (T)p.jitter;
+          }
+        }
+        out[r * p.ldo + cc] = val;
+      }
+    }
+    __syncthreads();  // yt (and, without the bulk engine, ys) are rewritten by the next tile
+  }
+}
+
 template <typename T>
 static int launch_kernel_matrix(const gpk_kernel_desc* desc, const T* xg, int64_t xg_gstride, int64_t x_bstride,
                                 int64_t n, const T* yg, int64_t yg_gstride, int64_t y_bstride, int64_t n2, int32_t d,
@@ -482,20 +619,22 @@ static int launch_kernel_matrix(const gpk_kernel_desc* desc, const T* xg, int64_
   const int kind0 = desc->fac_kind[0];
   if (!force_generic && desc->n_terms == 1 && desc->term_begin[1] - desc->term_begin[0] == 1 && kind0 >= GPK_EQ &&
       kind0 <= GPK_MATERN52 && desc->fac_group[0] >= 0 && desc->fac_group[0] < desc->n_groups) {
-    const size_t fsmem = ((size_t)2 * KM_TILE * d + (size_t)d * (KM_TILE + 1)) * sizeof(T);
+    static const bool one_tile = getenv("GPK_K1_ONE_TILE") != nullptr;
+    const size_t fsmem = ((size_t)(one_tile ? 2 : 3) * KM_TILE * d + (size_t)d * (KM_TILE + 1)) * sizeof(T);
     if (fsmem <= 96 * 1024) {
       void (*fk)(const KmParams) = nullptr;
       switch (kind0) {
-        case GPK_EQ: fk = kernel_matrix_fast_kernel<T, GPK_EQ>; break;
-        case GPK_MATERN12: fk = kernel_matrix_fast_kernel<T, GPK_MATERN12>; break;
-        case GPK_MATERN32: fk = kernel_matrix_fast_kernel<T, GPK_MATERN32>; break;
-        default: fk = kernel_matrix_fast_kernel<T, GPK_MATERN52>; break;
+        case GPK_EQ: fk = one_tile ? kernel_matrix_fast1_kernel<T, GPK_EQ> : kernel_matrix_fast_kernel<T, GPK_EQ>; break;
+        case GPK_MATERN12: fk = one_tile ? kernel_matrix_fast1_kernel<T, GPK_MATERN12> : kernel_matrix_fast_kernel<T, GPK_MATERN12>; break;
+        case GPK_MATERN32: fk = one_tile ? kernel_matrix_fast1_kernel<T, GPK_MATERN32> : kernel_matrix_fast_kernel<T, GPK_MATERN32>; break;
+        default: fk = one_tile ? kernel_matrix_fast1_kernel<T, GPK_MATERN52> : kernel_matrix_fast_kernel<T, GPK_MATERN52>; break;
       }
       if (fsmem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
         if (e != cudaSuccess) return -1000 - (int)e;
       }
-      fk<<<grid, KM_THREADS, fsmem, (cudaStream_t)stream>>>(p);
+      dim3 fgrid(one_tile ? grid.x : (grid.x + KM_STRIP - 1) / KM_STRIP, grid.y, grid.z);
+      fk<<<fgrid, KM_THREADS, fsmem, (cudaStream_t)stream>>>(p);
       GPK_COUNT_LAUNCH();
       GPK_CHECK_LAUNCH();
       return 0;
