@@ -442,6 +442,7 @@ constexpr int KM_STRIP = 8;  // column tiles per CTA of the fast kernel
 // fetched by the TMA engine (double-buffered, one mbarrier per buffer) while tile c is evaluated, so the bulk-copy latency,
 // the transposition and the barriers of a tile hide under the arithmetic of its predecessor (round-2 ncu of the
 // one-tile-per-CTA version: FP64 pipe 35 % busy with 3 CTAs per SM -- the per-tile prologue was as long as the tile's math).
+// n = 16384, lower: 0.499 ms against 0.585 ms for the one-tile kernel (1.22 ms for the generic descriptor kernel).
 template <typename T, int KIND>
 __global__ void __launch_bounds__(KM_THREADS, 3) kernel_matrix_fast_kernel(const KmParams p) {
   const int tile_r = blockIdx.y, b = blockIdx.z;
