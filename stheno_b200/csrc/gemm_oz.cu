@@ -7,7 +7,8 @@
 // (they are below the slicing error), leaving S(S+1)/2 int8 GEMMs -- 21 for S = 6 (error ~2^-40 of |a||b|, zero-mean), 28
 // for S = 7 (~2^-47) -- against the 8192 MAC/clk/SM of the int8 pipe instead of the 64 FMA/clk/SM of DMMA.
 //
-// 128 x 64 output tiles, a few consecutive tiles per CTA; products with the same s + t share an accumulator: S accumulators
+// 128 x 64 output tiles, a few consecutive tiles per CTA, enumerated in bands of tile rows, column-major inside a band (tiles
+// in flight share the band's A slices in L2; oz_tile); products with the same s + t share an accumulator: S accumulators
 // x 64 TMEM columns.  The producer and the issuer run ahead into the next tile while the epilogue warps finish the previous
 // one (TMEM full / empty mbarriers); only the accumulator drain itself (S x 64 columns at the 64 B/clk TMEM read rate,
 // ~1.9 us of 11.7 us per tile for S = 7) is serial.

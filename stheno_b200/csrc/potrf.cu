@@ -1,14 +1,18 @@
 // K2 / K3: blocked right-looking Cholesky (lower, row-major, in place) and the recursive triangular solve.
 //
 //   potrf      two-level blocking: 128-wide leaf steps inside 512-wide outer panels (GPK_NB_OUTER).  Per leaf step
-//                (1) potrf_leaf  : one CTA factorises the 128 x 128 diagonal block entirely in registers
-//                                  (cyclic 8 x 8 micro-tiles, one __syncthreads per column, log-det and info folded in)
+//                (1) potrf_leaf  : one CTA factorises the 128 x 128 diagonal block (log-det and info folded in): fp64 = the
+//                                  recursive shared-memory kernel (4 x 4 sub-blocks of 32 x 32, single-warp in-register
+//                                  factorisation of each diagonal sub-block, 33 us); fp32 = the register-tiled kernel
+//                                  (cyclic 8 x 8 micro-tiles, one __syncthreads per column, 30 us)
 //                (2) trsm_leaf   : all rows below (incl. the fused right-hand-side rows)  X L11^T = A21
 //                (3) gemm (K=128): update of the rest of the outer panel
 //              and per outer panel one big SYRK-style trailing update (K = 512), which carries > 90 % of the n^3/3 flops
 //              at n = 16384 with C read/written once per 512 columns: on the int8 tensor cores (fp64 emulated with exact
 //              integer slice products, gemm_oz.cu) when the caller enabled it, on the fp64 tensor cores (DMMA) otherwise
-//              (measured: 512 beats 256, 768, 1024 for both).
+//              (measured: 512 beats 256, 768, 1024 for both).  Emulated path, n_pad >= 4096: the FAR part of the trailing
+//              matrix is updated once per PAIR of panels with K = 1024 (potrf_driver_pairs): half the passes over the
+//              trailing matrix and half the TMEM drains per flop, the panels themselves unchanged.
 //              With look-ahead the next panel is factorised on two high-priority side streams while that update runs:
 //              `chain` = leaf -> 4-CTA solve of the next 128 rows -> 17-CTA update of the next diagonal block -> leaf ...
 //              (everything the next leaf depends on), `bulk` = all other rows of the block column, ordered by events.
