@@ -842,10 +842,9 @@ int oz_gemm_sliced(int64_t, int64_t, int64_t, double, const void*, int64_t, int6
 //   MODE_TF32X3  opt-in: fp32 copy of the panel, 3xTF32 products on tcgen05 (fp32-level products)
 //   MODE_OZAKI   int8 slices of the panel (error-free split), exact int32 products on tcgen05, fp64 recombination
 enum { MODE_F64 = 0, MODE_TF32X3 = 1, MODE_OZAKI = 2 };
-// scratch of the pair scheme: the pair's rows sliced 1024 wide (two buffers: the next pair is sliced on the side stream
-// while the far update still reads the current one) + one panel's rows sliced 512 wide
+// scratch of the pair scheme: the pair's rows sliced 1024 wide + one panel's rows sliced 512 wide
 static inline int64_t potrf_pairs_ws_bytes(int64_t R, int32_t S) {
-  return 2 * ((oz_ws_bytes(R, 1024, S) + 1023) & ~int64_t(1023)) + oz_ws_bytes(R, 512, S);
+  return ((oz_ws_bytes(R, 1024, S) + 1023) & ~int64_t(1023)) + oz_ws_bytes(R, 512, S);
 }
 struct Trailing {
   int mode = MODE_F64;
@@ -921,10 +920,8 @@ static int potrf_driver_pairs(double* A, int64_t lda, int64_t n_pad, int64_t ext
     if (nola) return factor_panel<double>(A, lda, 0, R, c0, c1, logdet, info, 1, stream);
     return factor_panel_split<double>(A, lda, 0, R, c0, c1, logdet, info, 1, side, la);  // ends joined with bulk
   };
-  const int64_t x_bytes = (oz_ws_bytes(R, 2 * P, S) + 1023) & ~int64_t(1023);
-  void* wsXb[2] = {ws, static_cast<char*>(ws) + x_bytes};  // [S][R][1024] + scales, double-buffered
-  void* wsY = static_cast<char*>(ws) + 2 * x_bytes;         // [S][R][512] + scales
-  int cur = 0;
+  void* wsX = ws;                                                                       // [S][R][1024] + scales
+  void* wsY = static_cast<char*>(ws) + ((oz_ws_bytes(R, 2 * P, S) + 1023) & ~int64_t(1023));  // [S][R][512] + scales
   int rc;
   auto upd = [&](void* w, int64_t K, int64_t rA, int64_t rB, int64_t M, int64_t N, double* C, int32_t lower,
                  cudaStream_t s) -> int {
@@ -939,15 +936,12 @@ static int potrf_driver_pairs(double* A, int64_t lda, int64_t n_pad, int64_t ext
     if ((rc = upd(wsY, a1, 0, 0, R - a1, b1 - a1, A + a1 * lda + a1, 1, stream))) return rc;
     if ((rc = factor_panel<double>(A, lda, 0, R, a1, b1, logdet, info, 1, stream))) return rc;
   }
-  // the first pair's operand is sliced on the caller's stream; every later one on the side stream right after its pair is
-  // factorised, into the other buffer, so that the slicing pass leaves the caller's stream (it sat between two far updates)
-  if (2 * P < n_pad && (rc = oz_slice_panel(A + 2 * P * lda, lda, R - 2 * P, 2 * P, wsXb[0], R, S, stream))) return rc;
   for (int64_t kb = 0; kb + 2 * P < n_pad; kb += 2 * P) {
-    void* wsX = wsXb[cur];
     const int64_t ke = kb + 2 * P;                                   // pair [kb, ke) is factorised
     const int64_t ke1 = ke + P < n_pad ? ke + P : n_pad;              // A' = [ke, ke1)
     const int64_t ke2 = ke + 2 * P < n_pad ? ke + 2 * P : n_pad;      // B' = [ke1, ke2) (may be empty)
     const int64_t W1 = ke1 - ke, W2 = ke2 - ke1, K2 = 2 * P;
+    if ((rc = oz_slice_panel(A + ke * lda + kb, lda, R - ke, K2, wsX, R, S, stream))) return rc;
     if ((rc = ce(cudaEventRecord(la.fork, stream)))) return rc;
     if ((rc = ce(cudaStreamWaitEvent(side, la.fork, 0)))) return rc;
     if ((rc = ce(cudaStreamWaitEvent(bulk, la.fork, 0)))) return rc;
@@ -965,14 +959,10 @@ static int potrf_driver_pairs(double* A, int64_t lda, int64_t n_pad, int64_t ext
       if ((rc = upd(wsY, W1, W2, 0, R - ke2, W2, A + ke2 * lda + ke1, 0, bulk))) return rc;
       if ((rc = factor(ke1, ke2))) return rc;
     }
-    if (ke + 2 * P < n_pad) {  // another pair follows (so [A' | B'] is a full 1024 columns): slice its operand now
-      if ((rc = oz_slice_panel(A + ke2 * lda + ke, lda, R - ke2, K2, wsXb[cur ^ 1], R, S, side))) return rc;
-    }
     if ((rc = ce(cudaEventRecord(la.join, side)))) return rc;
     // the far part: everything right of the next pair, K = 1024, on the caller's stream
     if ((rc = upd(wsX, K2, ke2 - ke, ke2 - ke, R - ke2, n_pad - ke2, A + ke2 * lda + ke2, 1, stream))) return rc;
     if ((rc = ce(cudaStreamWaitEvent(stream, la.join, 0)))) return rc;
-    cur ^= 1;
   }
   return 0;
 }
