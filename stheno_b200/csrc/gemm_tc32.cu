@@ -27,11 +27,14 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB per A tile
 constexpr int TC_GEMM_THREADS = 192;
 // BN = 128: stage = A, A_lo, B, B_lo = 64 KB, 3 stages.  BN = 256: stage = 16 + 16 + 32 + 32 = 96 KB, 2 stages -- the
 // same bytes in flight, but every staged byte feeds twice the MMA work (the kernel is bound by bytes-in-flight / latency).
-template <int BN>
+// ST = 1 (BN = 128): a single 64 KB stage per CTA, so that THREE CTAs share an SM (3 x 128 TMEM columns, 3 x 65 KB) -- the
+// pipelining then happens ACROSS CTAs, including each tile's prologue and epilogue, which a one-CTA-per-SM ring cannot hide.
+// For the many small K = 512 tiles of batched problems (config 3: tensor pipe 15 % busy with the 2-stage 128 x 256 kernel).
+template <int BN, int ST = ((BN == 128) ? 3 : 2)>
 struct TcCfg {
   static constexpr int B_BYTES = BN * TC_BK * 4;
   static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (BN == 128) ? 3 : 2;
+  static constexpr int STAGES = ST;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
 };
 
@@ -96,11 +99,11 @@ __device__ __forceinline__ float4 tf32_low_part(float4 v) {
 
 // CT = type of C: float (fp32 problems) or double (opt-in mixed precision: fp64 matrix, fp32 operands -- the
 // "tf32 where the user opts in" trailing update of the fp64 Cholesky).
-template <typename CT, int TC_BN>
+template <typename CT, int TC_BN, int TC_ST = ((TC_BN == 128) ? 3 : 2)>
 __global__ void __launch_bounds__(TC_GEMM_THREADS, 1)
 gemm_nt_f32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                       const TcParams p) {
-  using Cfg = TcCfg<TC_BN>;
+  using Cfg = TcCfg<TC_BN, TC_ST>;
   constexpr int TC_STAGES = Cfg::STAGES, TC_STAGE_BYTES = Cfg::STAGE_BYTES, TC_TILE_BYTES = TC_A_BYTES;
   constexpr int TC_B_BYTES = Cfg::B_BYTES;
   int tm, tn;
@@ -279,7 +282,7 @@ static bool make_map(CUtensorMap* m, const float* base, int64_t K, int64_t rows,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename CT, int BN>
+template <typename CT, int BN, int ST = ((BN == 128) ? 3 : 2)>
 static int launch_tc_bn(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, int64_t a_bs,
                         const float* B, int64_t ldb, int64_t b_bs, float beta, CT* C, int64_t ldc, int64_t c_bs,
                         int32_t lower, int32_t batch, cudaStream_t stream) {
@@ -287,14 +290,14 @@ static int launch_tc_bn(int64_t M, int64_t N, int64_t K, float alpha, const floa
   if (!make_map(&mA, A, K, M, lda, a_bs, batch, TC_BM) || !make_map(&mB, B, K, N, ldb, b_bs, batch, BN)) return 0;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_nt_f32_tc_kernel<CT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TcCfg<BN>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_nt_f32_tc_kernel<CT, BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TcCfg<BN, ST>::SMEM_BYTES);
     if (e != cudaSuccess) return -1000 - (int)e;
     attr_set = true;
   }
   TcParams p{alpha, beta, C, ldc, c_bs, (int32_t)K, lower, (int32_t)(M / TC_BM), (int32_t)(N / BN)};
   dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)batch);
-  gemm_nt_f32_tc_kernel<CT, BN><<<grid, TC_GEMM_THREADS, TcCfg<BN>::SMEM_BYTES, stream>>>(mA, mB, p);
+  gemm_nt_f32_tc_kernel<CT, BN, ST><<<grid, TC_GEMM_THREADS, TcCfg<BN, ST>::SMEM_BYTES, stream>>>(mA, mB, p);
   GPK_COUNT_LAUNCH();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return -1000 - (int)e;
@@ -307,6 +310,9 @@ static int launch_tc(int64_t M, int64_t N, int64_t K, float alpha, const float* 
                      int32_t batch, cudaStream_t stream) {
   // 128 x 256 tiles when there are enough of them to fill the machine (each staged byte feeds twice the MMA work)
   static const int force_bn = getenv("GPK_TC_BN") ? atoi(getenv("GPK_TC_BN")) : 0;
+  static const int one_stage = getenv("GPK_TC_STAGES1") ? atoi(getenv("GPK_TC_STAGES1")) : 0;  // experiment switch
+  if (one_stage == 1 || (one_stage == 2 && batch >= 16))
+    return launch_tc_bn<CT, 128, 1>(M, N, K, alpha, A, lda, a_bs, B, ldb, b_bs, beta, C, ldc, c_bs, lower, batch, stream);
   const bool wide = (force_bn == 256) || (force_bn == 0 && N % 256 == 0 && (M / TC_BM) * (N / 256) * batch >= 148);
   if (wide && N % 256 == 0)
     return launch_tc_bn<CT, 256>(M, N, K, alpha, A, lda, a_bs, B, ldb, b_bs, beta, C, ldc, c_bs, lower, batch, stream);
