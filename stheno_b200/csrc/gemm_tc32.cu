@@ -311,7 +311,9 @@ static int launch_tc(int64_t M, int64_t N, int64_t K, float alpha, const float* 
   // 128 x 256 tiles when there are enough of them to fill the machine (each staged byte feeds twice the MMA work)
   static const int force_bn = getenv("GPK_TC_BN") ? atoi(getenv("GPK_TC_BN")) : 0;
   static const int one_stage = getenv("GPK_TC_STAGES1") ? atoi(getenv("GPK_TC_STAGES1")) : 0;  // experiment switch
-  if (one_stage == 1 || (one_stage == 2 && batch >= 16))
+  if (one_stage == 3 && batch >= 16 && N % 256 == 0)  // 128 x 256 tiles, one 96 KB stage: two CTAs per SM
+    return launch_tc_bn<CT, 256, 1>(M, N, K, alpha, A, lda, a_bs, B, ldb, b_bs, beta, C, ldc, c_bs, lower, batch, stream);
+  if (one_stage == 1 || ((one_stage == 2 || one_stage == 3) && batch >= 16))
     return launch_tc_bn<CT, 128, 1>(M, N, K, alpha, A, lda, a_bs, B, ldb, b_bs, beta, C, ldc, c_bs, lower, batch, stream);
   const bool wide = (force_bn == 256) || (force_bn == 0 && N % 256 == 0 && (M / TC_BM) * (N / 256) * batch >= 148);
   if (wide && N % 256 == 0)

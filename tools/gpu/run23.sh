@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-for cfg in "GPK_TC_STAGES1=0" "GPK_TC_STAGES1=2"; do
+for cfg in "GPK_TC_STAGES1=2" "GPK_TC_STAGES1=3"; do
 env $cfg timeout 150 python - "$cfg" <<'P'
 import sys, torch
 sys.path.insert(0, ".")
@@ -18,4 +18,4 @@ for Bn in (64, 512):
 P
 done
 echo "== tests with the one-stage kernel for batched problems"
-GPK_TC_STAGES1=2 timeout 200 python -m pytest tests/test_configs.py tests/test_gpu_primitives.py -m gpu -q -x -p no:cacheprovider -k "config3 or gemm or fp32 or batch" 2>&1 | tail -3
+GPK_TC_STAGES1=3 timeout 200 python -m pytest tests/test_configs.py tests/test_gpu_primitives.py -m gpu -q -x -p no:cacheprovider -k "config3 or gemm or fp32 or batch" 2>&1 | tail -3
