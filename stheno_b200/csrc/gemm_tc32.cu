@@ -310,7 +310,10 @@ static int launch_tc(int64_t M, int64_t N, int64_t K, float alpha, const float* 
                      int32_t batch, cudaStream_t stream) {
   // 128 x 256 tiles when there are enough of them to fill the machine (each staged byte feeds twice the MMA work)
   static const int force_bn = getenv("GPK_TC_BN") ? atoi(getenv("GPK_TC_BN")) : 0;
-  static const int one_stage = getenv("GPK_TC_STAGES1") ? atoi(getenv("GPK_TC_STAGES1")) : 0;  // experiment switch
+  // batched problems (many small tiles): the one-stage 128 x 128 kernel, three CTAs per SM -- measured on config 3 (round 2):
+  // 64 x 2048: 4.28 -> 4.09 ms, 512 x 2048: 30.8 -> 28.3 ms, bit-identical results.  GPK_TC_STAGES1: 0 = never, 1 = always,
+  // 2 = batched (default), 3 = batched with 128 x 256 tiles / two CTAs per SM (28.7 ms)
+  static const int one_stage = getenv("GPK_TC_STAGES1") ? atoi(getenv("GPK_TC_STAGES1")) : 2;
   if (one_stage == 3 && batch >= 16 && N % 256 == 0)  // 128 x 256 tiles, one 96 KB stage: two CTAs per SM
     return launch_tc_bn<CT, 256, 1>(M, N, K, alpha, A, lda, a_bs, B, ldb, b_bs, beta, C, ldc, c_bs, lower, batch, stream);
   if (one_stage == 1 || ((one_stage == 2 || one_stage == 3) && batch >= 16))
